@@ -1,0 +1,244 @@
+/*
+ * mxadv.h — C ABI of libmxadv.so: B200-native (sm_100a, fp64) scalar-advection hot path of
+ * MAESTROeX: Godunov edge-state prediction (slopes / PPM / corner-coupled transverse terms /
+ * upwinding) and (rho X_k), (rho h) face-flux assembly, plus the 1-D base-state helpers.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * MAESTROeX tree, commit 543ea58f).  The reference has no FFI: these are the functions the
+ * source-shadowing overlay in maestroex_b200/overlay/ (same `Maestro::` member signatures)
+ * binds, see INTEGRATION.md.
+ *
+ * Conventions
+ *  - Plain pointers + POD structs only.  All floating point data is IEEE binary64.
+ *  - A fab (`MxFab`) is one box of an AMReX MultiFab in Array4 order
+ *    (external/amrex/Src/Base/AMReX_Array4.H:86-91): i fastest, then j, k, component slowest,
+ *    over the GHOST-GROWN box [lo,hi] (inclusive).  2-D data has lo[2] = hi[2] = 0.
+ *    value(i,j,k,n) = p[(i-lo[0]) + nx*((j-lo[1]) + ny*((k-lo[2]) + nz*n))].
+ *  - Face-centred fabs in direction d are indexed by the low-face convention
+ *    (face i sits between cells i-1 and i) and their valid box is [vlo, vhi + e_d].
+ *  - Pointers may be device pointers (AMReX built USE_CUDA=TRUE: The_Arena memory, or managed
+ *    memory as used by BaseState, Source/BaseState.H:300) or plain host pointers (CPU AMReX
+ *    build).  The library detects which (cudaPointerGetAttributes); host fabs are staged
+ *    through a library-owned device workspace (pinned double-buffered z-slabs).  There is no
+ *    CPU compute path: without a CUDA device every compute entry point fails with
+ *    MX_ERR_NO_DEVICE.
+ *  - Caller owns every buffer.  Outputs: only components [start_scomp, start_scomp+num_comp)
+ *    of `sedge`, the listed components of `sflux`, and `etarhoflux` (read-modify-write) are
+ *    written, and only on their valid (nodal) boxes; everything else is left untouched.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls on
+ *    device data are asynchronous on that stream; calls on host data return after the results
+ *    are back in host memory.
+ *  - Return value: 0 on success, negative MX_ERR_* otherwise; mx_last_error() returns a
+ *    thread-local message.  (The reference aborts via amrex::Abort; the overlay turns a
+ *    non-zero return into amrex::Abort(mx_last_error()).)
+ */
+#ifndef MXADV_H
+#define MXADV_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXADV_ABI_VERSION 1
+
+enum {
+    MX_OK = 0,
+    MX_ERR_INVALID = -1,     /* bad argument / inconsistent boxes */
+    MX_ERR_UNSUPPORTED = -2, /* option combination the reference itself rejects or that is
+                                not built (never a silent fallback) */
+    MX_ERR_CUDA = -3,        /* CUDA runtime error (message has the cudaError string) */
+    MX_ERR_NO_DEVICE = -4    /* no CUDA device: there is no CPU fallback */
+};
+
+/* AMReX mathematical BC codes, external/amrex/Src/Base/AMReX_BC_TYPES.H:68-76 */
+enum {
+    MX_BC_REFLECT_ODD = -1,
+    MX_BC_INT_DIR = 0,
+    MX_BC_REFLECT_EVEN = 1,
+    MX_BC_FOEXTRAP = 2,
+    MX_BC_EXT_DIR = 3,
+    MX_BC_HOEXTRAP = 4
+};
+
+/* species_pred_type / enthalpy_pred_type, Source/MaestroMakeFlux.cpp:6-16 */
+enum { MX_PRED_RHOPRIME_AND_X = 1, MX_PRED_RHOX = 2, MX_PRED_RHO_AND_X = 3 };
+enum {
+    MX_PRED_RHOH = 0,
+    MX_PRED_RHOHPRIME = 1,
+    MX_PRED_H = 2,
+    MX_PRED_T_THEN_RHOHPRIME = 3,
+    MX_PRED_T_THEN_H = 4,
+    MX_PRED_HPRIME = 5,
+    MX_PRED_TPRIME_THEN_H = 6
+};
+
+/* One box of a MultiFab: mf[mfi].dataPtr(), mf[mfi].box(), mf.nComp()
+ * (external/amrex/Src/Base/AMReX_BaseFab.H:277,291,352). */
+typedef struct MxFab {
+    double* p;
+    int lo[3];
+    int hi[3];
+    int ncomp;
+} MxFab;
+
+/* Index space: mfi.validbox(), geom[lev].Domain(), geom[lev].CellSizeArray(). */
+typedef struct MxGeom {
+    int dim;         /* AMREX_SPACEDIM: 2 or 3 */
+    int valid_lo[3]; /* cell-centred valid box of this fab */
+    int valid_hi[3];
+    int dom_lo[3]; /* cell-centred problem domain */
+    int dom_hi[3];
+    double dx[3];
+} MxGeom;
+
+/* A BaseState<Real> viewed as BaseStateArray (Source/BaseState.H:14-81):
+ * value(lev, r, n) = p[(lev*len + r)*nvar + n]. */
+typedef struct MxBase {
+    const double* p;
+    int nlev;
+    int len;
+    int nvar;
+} MxBase;
+
+/* Arguments + runtime parameters of Maestro::MakeEdgeScal
+ * (Source/MaestroMakeEdgeScalars.cpp:6-12; maestro.* parameters from
+ * Source/param/_cpp_parameters; dt and rel_eps are Maestro members, Source/Maestro.H:1873,1974). */
+typedef struct MxEdgeParams {
+    double dt;
+    double rel_eps;
+    int ppm_type;         /* 0 (slopes), 1 (CW84), 2 (Colella-Sekora 2008) */
+    int slope_order;      /* 0, 2, 4 (used when ppm_type == 0) */
+    int ppm_trace_forces; /* 0 / 1 */
+    int is_vel;
+    int is_conservative;
+    int start_scomp;  /* first component of state/force/sedge to sweep */
+    int start_bccomp; /* first entry of bc[] to use */
+    int num_comp;
+    int nbccomp;   /* number of BCRec entries in bc */
+    const int* bc; /* HOST pointer, nbccomp x 6: {lo_x,lo_y,lo_z,hi_x,hi_y,hi_z} per BCRec */
+} MxEdgeParams;
+
+/* Runtime parameters + state indices used by MakeRhoXFlux / MakeRhoHFlux
+ * (Source/MaestroMakeFlux.cpp:35-37,495-504; state_indices.H from Source/param/_variables). */
+typedef struct MxFluxParams {
+    int species_pred_type;
+    int enthalpy_pred_type;
+    int spherical;
+    int use_exact_base_state;
+    int evolve_base_state;
+    int rho_comp;   /* Rho */
+    int rhoh_comp;  /* RhoH */
+    int first_spec; /* FirstSpec */
+    int num_spec;   /* NumSpec */
+    int start_comp; /* MakeRhoXFlux: first species component to flux */
+    int num_comp;   /* MakeRhoXFlux: number of components */
+    int lev;        /* level index into the BaseState arrays */
+} MxFluxParams;
+
+/* ---- library / device management ------------------------------------------------------ */
+
+int mx_abi_version(void);
+const char* mx_last_error(void);
+/* Number of CUDA devices visible (0 if none / no driver); never fails. */
+int mx_device_count(void);
+/* Number of kernels this library has launched since load (or since mx_reset_launch_count). */
+long long mx_launch_count(void);
+void mx_reset_launch_count(void);
+/* Release the cached device workspaces. */
+int mx_free_workspace(void);
+
+/* ---- Maestro::MakeEdgeScal ---------------------------------------------------------------
+ * Replaces Maestro::MakeEdgeScal (Source/MaestroMakeEdgeScalars.cpp:6-302, decl
+ * Source/Maestro.H:913-919) for ONE box of ONE level, including everything it calls:
+ * Slopex/y/z (MaestroSlopes.cpp), PPM (MaestroPPM.cpp), MakeDivU, MakeEdgeScalPredictor,
+ * MakeEdgeScalTransverse, MakeEdgeScalEdges.  state: >= 3 ghost cells (4 if ppm_type == 2);
+ * umac[d]: face-centred in d, 1 ghost; force: 1 ghost (state's ghosts if ppm_trace_forces);
+ * sedge[d]: face-centred in d, any ghosts.  AverageDownFaces (is_vel only) is the caller's. */
+int mx_make_edge_scal(const MxGeom* geom, const MxFab* state, const MxFab* sedge /*[dim]*/,
+                      const MxFab* umac /*[dim]*/, const MxFab* force,
+                      const MxEdgeParams* par, void* stream);
+
+/* ---- Maestro::MakeRhoXFlux ---------------------------------------------------------------
+ * Replaces Maestro::MakeRhoXFlux (Source/MaestroMakeFlux.cpp:18-465, decl Maestro.H:230-245)
+ * for one box: zeroes sflux(Rho), computes the species fluxes, sums them into sflux(Rho) and
+ * accumulates etarhoflux on the vertical faces.  r0mac_old/new (3 fabs each) are only read
+ * when par->spherical; pass NULL otherwise.  Flux registers / AverageDownFaces (AMR) stay
+ * with the caller. */
+int mx_make_rhoX_flux(const MxGeom* geom, const MxFab* sflux /*[dim]*/,
+                      const MxFab* etarhoflux, const MxFab* sedge /*[dim]*/,
+                      const MxFab* umac /*[dim]*/, const MxBase* rho0_old,
+                      const MxBase* rho0_edge_old, const MxFab* r0mac_old /*[3] or NULL*/,
+                      const MxBase* rho0_new, const MxBase* rho0_edge_new,
+                      const MxFab* r0mac_new /*[3] or NULL*/,
+                      const MxBase* rho0_predicted_edge, const MxBase* w0,
+                      const MxFluxParams* par, void* stream);
+
+/* ---- Maestro::MakeRhoHFlux ---------------------------------------------------------------
+ * Replaces Maestro::MakeRhoHFlux (Source/MaestroMakeFlux.cpp:467-1067, decl
+ * Maestro.H:270-295) for one box.  The *mac fabs are only read when par->spherical. */
+int mx_make_rhoh_flux(const MxGeom* geom, const MxFab* sflux /*[dim]*/,
+                      const MxFab* sedge /*[dim]*/, const MxFab* umac /*[dim]*/,
+                      const MxBase* rho0_old, const MxBase* rho0_edge_old,
+                      const MxFab* r0mac_old, const MxBase* rho0_new,
+                      const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                      const MxBase* rhoh0_old, const MxBase* rhoh0_edge_old,
+                      const MxFab* rh0mac_old, const MxBase* rhoh0_new,
+                      const MxBase* rhoh0_edge_new, const MxFab* rh0mac_new,
+                      const MxFab* h0mac_old, const MxFab* h0mac_new,
+                      const MxFluxParams* par, void* stream);
+
+/* ---- fused density / enthalpy passes -----------------------------------------------------
+ * What DensityAdvance does between Source/MaestroDensityAdvance.cpp:115 and :217 in one
+ * pass over the data: MakeEdgeScal(species X_k) + MakeEdgeScal(rho' or rho) + MakeRhoXFlux.
+ * `state` holds X_k in the species components and rho' (or rho) in Rho, i.e. the state as it
+ * is after ConvertRhoXToX / PutInPertForm (:98-104).  `epar` describes the species sweep
+ * (start_scomp = FirstSpec, num_comp = NumSpec, start_bccomp = FirstSpec); Rho is swept with
+ * BCRec index `rho_bccomp`.  Requires 3-D, is_vel = 0, is_conservative = 0,
+ * species_pred_type 1 or 3.  Results are bit-identical to the three separate calls. */
+int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                         const MxFab* sflux, const MxFab* etarhoflux, const MxFab* umac,
+                         const MxFab* force, const MxEdgeParams* epar, int rho_bccomp,
+                         const MxBase* rho0_old, const MxBase* rho0_edge_old,
+                         const MxFab* r0mac_old, const MxBase* rho0_new,
+                         const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                         const MxBase* rho0_predicted_edge, const MxBase* w0,
+                         const MxFluxParams* fpar, void* stream);
+
+/* EnthalpyAdvance's MakeEdgeScal(pred_comp) + MakeRhoHFlux
+ * (Source/MaestroEnthalpyAdvance.cpp:141-146,229,312) in one pass; epar sweeps the single
+ * component RhoH (enthalpy_pred_type 0/1/2/5) and reads sedge(Rho) where the flux form needs
+ * it.  3-D planar only. */
+int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                          const MxFab* sflux, const MxFab* umac, const MxFab* force,
+                          const MxEdgeParams* epar, const MxBase* rho0_old,
+                          const MxBase* rho0_edge_old, const MxBase* rho0_new,
+                          const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
+                          const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+                          const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
+                          void* stream);
+
+/* ---- Maestro::CelltoEdge -----------------------------------------------------------------
+ * Replaces Maestro::CelltoEdge (Source/MaestroCelltoEdge.cpp:5-55) for one radial level with
+ * one disjoint chunk covering [r_lo, r_hi] (base_geom.r_start_coord / r_end_coord) of nr
+ * cells: cell has nr entries, edge nr+1.  Planar only (the reference aborts if spherical). */
+int mx_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi,
+                    void* stream);
+
+/* ---- ghost-cell exchange between the bricks of one box (multi-GPU) -----------------------
+ * Packs / unpacks the `ng`-deep face slab `side` (0 = lo, 1 = hi) of direction `dir` of
+ * components [comp0, comp0+ncomp) of a fab into / from a contiguous device buffer, i.e. the
+ * FB_local_copy_gpu step of FabArray::FillBoundary
+ * (external/amrex/Src/Base/AMReX_FabArrayCommI.H:49-150); the transfer itself is an NCCL
+ * send/recv (or P2P copy) issued by the host layer.  `interior` = 1 packs the valid cells
+ * adjacent to the face (what a neighbour needs), 0 unpacks into the ghost cells. */
+int mx_halo_pack(const MxGeom* geom, const MxFab* fab, int dir, int side, int ng, int comp0,
+                 int ncomp, double* buf, void* stream);
+int mx_halo_unpack(const MxGeom* geom, const MxFab* fab, int dir, int side, int ng,
+                   int comp0, int ncomp, const double* buf, void* stream);
+/* Number of doubles mx_halo_pack writes for these arguments. */
+long long mx_halo_count(const MxGeom* geom, const MxFab* fab, int dir, int ng, int ncomp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXADV_H */

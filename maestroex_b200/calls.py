@@ -1,0 +1,97 @@
+"""Uniform Python call layer over the C ABI declared in include/mxadv.h.
+
+``Calls(lib, prefix, with_stream)`` wraps a loaded shared library whose entry points are
+``<prefix>make_edge_scal`` etc.  The product library uses prefix ``mx_`` and takes a trailing
+``void* stream``; the test-only oracle / reference libraries use ``orc_`` / ``ref_`` and the
+same argument lists without the stream (see oracle/backends.py).
+Argument order and meaning follow the reference member functions
+(Source/MaestroMakeEdgeScalars.cpp:6, Source/MaestroMakeFlux.cpp:18,467,
+Source/MaestroCelltoEdge.cpp:5).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from .abi import Base, EdgeParams, Fab, FluxParams, Geom, fab_array
+
+
+class MxError(RuntimeError):
+    pass
+
+
+class Calls:
+    def __init__(self, lib: C.CDLL, prefix: str, with_stream: bool):
+        self.lib = lib
+        self.prefix = prefix
+        self.with_stream = with_stream
+
+    # -- helpers ----------------------------------------------------------------------
+    def _fn(self, name):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+    def _check(self, rc, name):
+        if rc != 0:
+            msg = ""
+            if self.prefix == "mx_":
+                self.lib.mx_last_error.restype = C.c_char_p
+                msg = self.lib.mx_last_error().decode()
+            raise MxError(f"{self.prefix}{name} failed with code {rc}: {msg}")
+
+    def _tail(self, stream):
+        return (C.c_void_p(stream),) if self.with_stream else ()
+
+    @staticmethod
+    def _faces(fabs):
+        return fab_array(fabs) if fabs is not None else None
+
+    @staticmethod
+    def _base(b):
+        return C.byref(b.c()) if b is not None else None
+
+    # -- Maestro::MakeEdgeScal --------------------------------------------------------
+    def make_edge_scal(self, geom: Geom, state: Fab, sedge, umac, force: Fab,
+                       par: EdgeParams, stream: int = 0):
+        g, st, fo, p = geom.c(), state.c(), force.c(), par.c()
+        rc = self._fn("make_edge_scal")(C.byref(g), C.byref(st), self._faces(sedge),
+                                        self._faces(umac), C.byref(fo), C.byref(p),
+                                        *self._tail(stream))
+        self._check(rc, "make_edge_scal")
+
+    # -- Maestro::MakeRhoXFlux --------------------------------------------------------
+    def make_rhoX_flux(self, geom: Geom, sflux, etarhoflux: Fab, sedge, umac,
+                       rho0_old: Base, rho0_edge_old: Base, r0mac_old, rho0_new: Base,
+                       rho0_edge_new: Base, r0mac_new, rho0_predicted_edge: Base, w0: Base,
+                       par: FluxParams, stream: int = 0):
+        g, eta, p = geom.c(), etarhoflux.c(), par.c()
+        rc = self._fn("make_rhoX_flux")(
+            C.byref(g), self._faces(sflux), C.byref(eta), self._faces(sedge),
+            self._faces(umac), self._base(rho0_old), self._base(rho0_edge_old),
+            self._faces(r0mac_old), self._base(rho0_new), self._base(rho0_edge_new),
+            self._faces(r0mac_new), self._base(rho0_predicted_edge), self._base(w0),
+            C.byref(p), *self._tail(stream))
+        self._check(rc, "make_rhoX_flux")
+
+    # -- Maestro::MakeRhoHFlux --------------------------------------------------------
+    def make_rhoh_flux(self, geom: Geom, sflux, sedge, umac, rho0_old, rho0_edge_old,
+                       r0mac_old, rho0_new, rho0_edge_new, r0mac_new, rhoh0_old,
+                       rhoh0_edge_old, rh0mac_old, rhoh0_new, rhoh0_edge_new, rh0mac_new,
+                       h0mac_old, h0mac_new, par: FluxParams, stream: int = 0):
+        g, p = geom.c(), par.c()
+        rc = self._fn("make_rhoh_flux")(
+            C.byref(g), self._faces(sflux), self._faces(sedge), self._faces(umac),
+            self._base(rho0_old), self._base(rho0_edge_old), self._faces(r0mac_old),
+            self._base(rho0_new), self._base(rho0_edge_new), self._faces(r0mac_new),
+            self._base(rhoh0_old), self._base(rhoh0_edge_old), self._faces(rh0mac_old),
+            self._base(rhoh0_new), self._base(rhoh0_edge_new), self._faces(rh0mac_new),
+            self._faces(h0mac_old), self._faces(h0mac_new), C.byref(p), *self._tail(stream))
+        self._check(rc, "make_rhoh_flux")
+
+    # -- Maestro::CelltoEdge ----------------------------------------------------------
+    def cell_to_edge(self, cell, edge, nr: int, r_lo: int, r_hi: int, stream: int = 0):
+        from .abi import _ptr_of
+        rc = self._fn("cell_to_edge")(C.c_void_p(_ptr_of(cell)), C.c_void_p(_ptr_of(edge)),
+                                      C.c_int(nr), C.c_int(r_lo), C.c_int(r_hi),
+                                      *self._tail(stream))
+        self._check(rc, "cell_to_edge")

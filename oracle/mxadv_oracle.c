@@ -1,0 +1,1044 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — CPU oracle for the MAESTROeX scalar-advection hot path.
+ *
+ * A plain-C restatement (our own code, direction-generic, flat arrays) of the reference
+ * algorithm.  It is the checker for tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg; the product (libmxadv.so) never links, loads or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks it bit-for-bit against
+ * oracle/_ref/libmaestro_ref{2,3}d.so, which is the reference's own
+ * Source/Maestro{MakeEdgeScalars,PPM,Slopes,MakeFlux,CelltoEdge}.cpp compiled unmodified
+ * (oracle/Makefile), and against the golden vectors under tests/golden/ generated from that
+ * library (tests/golden/make_golden.py).
+ *
+ * Compile with -ffp-contract=off (no FMA): the reference CPU build has none either
+ * (g++ -O3 without -march), and every expression below keeps the reference's association.
+ *
+ * Reference files followed (relative to the MAESTROeX tree):
+ *   Source/MaestroSlopes.cpp:6-601          -> slope_dir()
+ *   Source/MaestroPPM.cpp:6-2263            -> ppm_dir()
+ *   Source/MaestroMakeEdgeScalars.cpp:6-302 -> orc_make_edge_scal() (driver)
+ *     :306-452 / :662-863                   -> predictor_dir()  (2-D / 3-D)
+ *     :648-660                              -> MakeDivU in orc_make_edge_scal()
+ *     :865-1359                             -> transverse()
+ *     :454-644 / :1361-1667                 -> edges_dir()      (2-D / 3-D)
+ *   Source/MaestroMakeFlux.cpp:18-465       -> orc_make_rhoX_flux()
+ *   Source/MaestroMakeFlux.cpp:467-1067     -> orc_make_rhoh_flux()
+ *   Source/MaestroCelltoEdge.cpp:5-55       -> orc_cell_to_edge()
+ * Direction-dependent quirks of the reference that are reproduced on purpose are marked
+ * "QUIRK" with the file:line they come from.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/mxadv.h"
+
+#define BC_REFLECT_ODD (-1)
+#define BC_REFLECT_EVEN 1
+#define BC_FOEXTRAP 2
+#define BC_EXT_DIR 3
+#define BC_HOEXTRAP 4
+
+/* std::min / std::max semantics (amrex::min/max), not fmin/fmax */
+static inline double dmin(double a, double b) { return (b < a) ? b : a; }
+static inline double dmax(double a, double b) { return (a < b) ? b : a; }
+
+typedef struct {
+    int lo[3], hi[3];
+} IBox;
+
+static IBox grow_all(IBox b, int n, int dim) {
+    for (int d = 0; d < dim; ++d) { b.lo[d] -= n; b.hi[d] += n; }
+    return b;
+}
+
+/* strided view of one component of a fab */
+typedef struct {
+    const double* p; /* points at (lo) of the chosen component */
+    long st[3];
+    int lo[3];
+} CView;
+
+static CView cview(const MxFab* f, int comp) {
+    CView v;
+    long nx = f->hi[0] - f->lo[0] + 1, ny = f->hi[1] - f->lo[1] + 1,
+         nz = f->hi[2] - f->lo[2] + 1;
+    v.p = f->p + (long)comp * nx * ny * nz;
+    v.st[0] = 1; v.st[1] = nx; v.st[2] = nx * ny;
+    for (int d = 0; d < 3; ++d) v.lo[d] = f->lo[d];
+    return v;
+}
+static inline long voff(const CView* v, int i, int j, int k) {
+    return (i - v->lo[0]) * v->st[0] + (j - v->lo[1]) * v->st[1] + (k - v->lo[2]) * v->st[2];
+}
+#define RD(v, i, j, k) ((v).p[voff(&(v), (i), (j), (k))])
+
+/* scratch array on a box */
+typedef struct {
+    double* p;
+    long st[3];
+    int lo[3];
+} Tmp;
+static Tmp tmp_alloc(IBox b) {
+    Tmp t;
+    long n0 = b.hi[0] - b.lo[0] + 1, n1 = b.hi[1] - b.lo[1] + 1, n2 = b.hi[2] - b.lo[2] + 1;
+    t.p = (double*)calloc((size_t)(n0 * n1 * n2), sizeof(double));
+    t.st[0] = 1; t.st[1] = n0; t.st[2] = n0 * n1;
+    for (int d = 0; d < 3; ++d) t.lo[d] = b.lo[d];
+    return t;
+}
+static inline long toff(const Tmp* t, int i, int j, int k) {
+    return (i - t->lo[0]) + (j - t->lo[1]) * t->st[1] + (k - t->lo[2]) * t->st[2];
+}
+#define T(t, i, j, k) ((t).p[toff(&(t), (i), (j), (k))])
+
+typedef struct {
+    int dim;
+    IBox valid, obx;
+    int domlo[3], domhi[3];
+    double dx[3];
+    double dt, rel_eps;
+    int ppm_type, slope_order, ppm_trace_forces, is_vel, is_cons;
+} Ctx;
+
+/* ------------------------------------------------------------------------------------ */
+/* Slopex/y/z: Source/MaestroSlopes.cpp:6-203 (x), :205-401 (y), :403-601 (z)             */
+/* ------------------------------------------------------------------------------------ */
+static void slope_dir(const Ctx* c, int d, const CView* s, Tmp* out, int bclo, int bchi) {
+    const int e0 = d == 0, e1 = d == 1, e2 = d == 2;
+    const int lo = c->domlo[d], hi = c->domhi[d];
+    const int lobc = (bclo == BC_EXT_DIR || bclo == BC_HOEXTRAP);
+    const int hibc = (bchi == BC_EXT_DIR || bchi == BC_HOEXTRAP);
+    for (int k = c->obx.lo[2]; k <= c->obx.hi[2]; ++k)
+    for (int j = c->obx.lo[1]; j <= c->obx.hi[1]; ++j)
+    for (int i = c->obx.lo[0]; i <= c->obx.hi[0]; ++i) {
+#define S(o) RD(*s, i + (o) * e0, j + (o) * e1, k + (o) * e2)
+        const int I = d == 0 ? i : (d == 1 ? j : k);
+        double r;
+        if (c->slope_order == 0) {
+            r = 0.0; /* MaestroSlopes.cpp:35-38 */
+        } else if (c->slope_order == 2) {
+            /* MaestroSlopes.cpp:43-90 */
+            double del = 0.5 * (S(1) - S(-1));
+            double dpls = 2.0 * (S(1) - S(0));
+            double dmn = 2.0 * (S(0) - S(-1));
+            double slim = dmin(fabs(dpls), fabs(dmn));
+            slim = dpls * dmn > 0.0 ? slim : 0.0;
+            double sflag = copysign(1.0, del);
+            r = sflag * dmin(slim, fabs(del));
+            if (lobc) {
+                if (I == lo - 1) {
+                    r = 0.0;
+                } else if (I == lo) {
+                    del = (S(1) + 3.0 * S(0) - 4.0 * S(-1)) / 3.0;
+                    dpls = 2.0 * (S(1) - S(0));
+                    dmn = 2.0 * (S(0) - S(-1));
+                    slim = dmin(fabs(dpls), fabs(dmn));
+                    slim = dpls * dmn > 0.0 ? slim : 0.0;
+                    sflag = copysign(1.0, del);
+                    r = sflag * dmin(slim, fabs(del));
+                }
+            }
+            if (hibc) {
+                if (I == hi + 1) {
+                    r = 0.0;
+                } else if (I == hi) {
+                    del = -(S(-1) + 3.0 * S(0) - 4.0 * S(1)) / 3.0;
+                    dpls = 2.0 * (S(1) - S(0));
+                    dmn = 2.0 * (S(0) - S(-1));
+                    slim = dmin(fabs(dpls), fabs(dmn));
+                    slim = dpls * dmn > 0.0 ? slim : 0.0;
+                    sflag = copysign(1.0, del);
+                    r = sflag * dmin(slim, fabs(del));
+                }
+            }
+        } else {
+            /* 4th order, MaestroSlopes.cpp:95-201 */
+            double dcen = 0.5 * (S(0) - S(-2));
+            double dmn = 2.0 * (S(-1) - S(-2));
+            double dpls = 2.0 * (S(0) - S(-1));
+            double dlim = dmin(fabs(dmn), fabs(dpls));
+            dlim = dpls * dmn > 0.0 ? dlim : 0.0;
+            double dflag = copysign(1.0, dcen);
+            double dxl = dflag * dmin(dlim, fabs(dcen));
+
+            dcen = 0.5 * (S(2) - S(0));
+            dmn = 2.0 * (S(1) - S(0));
+            dpls = 2.0 * (S(2) - S(1));
+            dlim = dmin(fabs(dmn), fabs(dpls));
+            dlim = dpls * dmn > 0.0 ? dlim : 0.0;
+            dflag = copysign(1.0, dcen);
+            double dxr = dflag * dmin(dlim, fabs(dcen));
+
+            dcen = 0.5 * (S(1) - S(-1));
+            dmn = 2.0 * (S(0) - S(-1));
+            dpls = 2.0 * (S(1) - S(0));
+            dlim = dmin(fabs(dmn), fabs(dpls));
+            dlim = dpls * dmn > 0.0 ? dlim : 0.0;
+            dflag = copysign(1.0, dcen);
+
+            double ds = 4.0 / 3.0 * dcen - (dxr + dxl) / 6.0;
+            r = dflag * dmin(fabs(ds), dlim);
+
+            /* QUIRK: in the one-sided rows Slopex selects `dlim` (the centred limiter
+             * computed above) where Slopey/Slopez select the freshly computed `slim`
+             * (MaestroSlopes.cpp:142,156,178,192 vs :341,355,377,391 and :539,...). */
+#define SEL_LIM(slim) (dpls * dmn > 0.0 ? (d == 0 ? dlim : (slim)) : 0.0)
+            if (lobc) {
+                if (I == lo - 1) {
+                    r = 0.0;
+                } else if (I == lo) {
+                    double del = -16.0 / 15.0 * S(-1) + 0.5 * S(0) + 2.0 / 3.0 * S(1) -
+                                 0.1 * S(2);
+                    dmn = 2.0 * (S(0) - S(-1));
+                    dpls = 2.0 * (S(1) - S(0));
+                    double slim = dmin(fabs(dpls), fabs(dmn));
+                    slim = SEL_LIM(slim);
+                    double sflag = copysign(1.0, del);
+                    r = sflag * dmin(slim, fabs(del));
+                } else if (I == lo + 1) {
+                    double del = -16.0 / 15.0 * S(-2) + 0.5 * S(-1) + 2.0 / 3.0 * S(0) -
+                                 0.1 * S(1);
+                    dmn = 2.0 * (S(-1) - S(-2));
+                    dpls = 2.0 * (S(0) - S(-1));
+                    double slim = dmin(fabs(dpls), fabs(dmn));
+                    slim = SEL_LIM(slim);
+                    double sflag = copysign(1.0, del);
+                    dxl = sflag * dmin(slim, fabs(del));
+                    ds = 4.0 / 3.0 * dcen - (dxr + dxl) / 6.0;
+                    r = dflag * dmin(fabs(ds), dlim);
+                }
+            }
+            if (hibc) {
+                if (I == hi + 1) {
+                    r = 0.0;
+                } else if (I == hi) {
+                    double del = -(-16.0 / 15.0 * S(1) + 0.5 * S(0) + 2.0 / 3.0 * S(-1) -
+                                   0.1 * S(-2));
+                    dmn = 2.0 * (S(0) - S(-1));
+                    dpls = 2.0 * (S(1) - S(0));
+                    double slim = dmin(fabs(dpls), fabs(dmn));
+                    slim = SEL_LIM(slim);
+                    double sflag = copysign(1.0, del);
+                    r = sflag * dmin(slim, fabs(del));
+                } else if (I == hi - 1) {
+                    double del = -(-16.0 / 15.0 * S(2) + 0.5 * S(1) + 2.0 / 3.0 * S(0) -
+                                   0.1 * S(-1));
+                    dmn = 2.0 * (S(1) - S(0));
+                    dpls = 2.0 * (S(2) - S(1));
+                    double slim = dmin(fabs(dpls), fabs(dmn));
+                    slim = SEL_LIM(slim);
+                    double sflag = copysign(1.0, del);
+                    dxr = sflag * dmin(slim, fabs(del));
+                    ds = 4.0 / 3.0 * dcen - (dxl + dxr) / 6.0;
+                    r = dflag * dmin(fabs(ds), dlim);
+                }
+            }
+#undef SEL_LIM
+        }
+        T(*out, i, j, k) = r;
+#undef S
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* PPM: Source/MaestroPPM.cpp:27-771 (x), :773-1513 (y), :1515-2262 (z), is_umac = true   */
+/* ------------------------------------------------------------------------------------ */
+static inline double vanleer(double sm1, double s0, double sp1) {
+    /* MaestroPPM.cpp:42-49 */
+    double dsc = 0.5 * (sp1 - sm1);
+    double dsl = 2.0 * (s0 - sm1);
+    double dsr = 2.0 * (sp1 - s0);
+    if (dsl * dsr > 0.0) return copysign(1.0, dsc) * dmin(fabs(dsc), dmin(fabs(dsl), fabs(dsr)));
+    return 0.0;
+}
+
+static inline void cw_limit(double s0, double* sm, double* sp) {
+    /* MaestroPPM.cpp:106-115 */
+    if ((*sp - s0) * (s0 - *sm) <= 0.0) {
+        *sp = s0;
+        *sm = s0;
+    } else if (fabs(*sp - s0) >= 2.0 * fabs(*sm - s0)) {
+        *sp = 3.0 * s0 - 2.0 * *sm;
+    } else if (fabs(*sm - s0) >= 2.0 * fabs(*sp - s0)) {
+        *sm = 3.0 * s0 - 2.0 * *sp;
+    }
+}
+
+static inline double bc_edge(double a, double b, double cc, double dd, double mn0, double mn1) {
+    /* -0.2 a + 0.75 b + 0.5 c - 0.05 d clamped between mn0, mn1: MaestroPPM.cpp:124-131 */
+    double v = -0.2 * a + 0.75 * b + 0.5 * cc - 0.05 * dd;
+    v = dmax(v, dmin(mn0, mn1));
+    v = dmin(v, dmax(mn0, mn1));
+    return v;
+}
+
+/* 4th-order edge with 2nd-derivative limiter, MaestroPPM.cpp:258-279; sm2..sp1 are the
+ * four cells around the edge between s_m1 and s_0 */
+static inline double cs_edge(double sm2, double sm1, double s0, double sp1) {
+    const double C = 1.25;
+    double e = (7.0 / 12.0) * (sm1 + s0) - (1.0 / 12.0) * (sm2 + sp1);
+    if ((e - sm1) * (s0 - e) < 0.0) {
+        double D2 = 3.0 * (sm1 - 2.0 * e + s0);
+        double D2L = sm2 - 2.0 * sm1 + s0;
+        double D2R = sm1 - 2.0 * s0 + sp1;
+        double sgn = copysign(1.0, D2);
+        double D2LIM = sgn * dmax(dmin(C * sgn * D2L, dmin(C * sgn * D2R, sgn * D2)), 0.0);
+        e = 0.5 * (sm1 + s0) - D2LIM / 6.0;
+    }
+    return e;
+}
+
+/* Colella-Sekora limiter, MaestroPPM.cpp:356-441 (and the BC re-applications :488-580,
+ * :627-718).  `big_thresh` is 1.e-10 except for the QUIRK noted at the call site. */
+static inline void cs_limit(double sedgel, double sedge, double sedger, double sedgerr,
+                            double sm2, double sm1, double s0, double sp1, double sp2,
+                            double bigm_thresh, double* sm_out, double* sp_out) {
+    const double C = 1.25;
+    double alphap = sedger - s0;
+    double alpham = sedge - s0;
+    int bigp = fabs(alphap) > 2.0 * fabs(alpham);
+    int bigm = fabs(alpham) > 2.0 * fabs(alphap);
+    int extremum = 0;
+    if (alpham * alphap >= 0.0) {
+        extremum = 1;
+    } else if (bigp || bigm) {
+        double dafacem = sedge - sedgel;
+        double dafacep = sedgerr - sedger;
+        double dabarm = s0 - sm1;
+        double dabarp = sp1 - s0;
+        double dafacemin = dmin(fabs(dafacem), fabs(dafacep));
+        double dabarmin = dmin(fabs(dabarm), fabs(dabarp));
+        double dachkm, dachkp;
+        if (dafacemin >= dabarmin) {
+            dachkm = dafacem;
+            dachkp = dafacep;
+        } else {
+            dachkm = dabarm;
+            dachkp = dabarp;
+        }
+        extremum = (dachkm * dachkp <= 0.0);
+    }
+    if (extremum) {
+        double D2 = 6.0 * (alpham + alphap);
+        double D2L = sm2 - 2.0 * sm1 + s0;
+        double D2R = s0 - 2.0 * sp1 + sp2;
+        double D2C = sm1 - 2.0 * s0 + sp1;
+        double sgn = copysign(1.0, D2);
+        double D2LIM =
+            dmax(dmin(sgn * D2, dmin(C * sgn * D2L, dmin(C * sgn * D2R, C * sgn * D2C))), 0.0);
+        double D2ABS = dmax(fabs(D2), 1.e-10);
+        alpham = alpham * D2LIM / D2ABS;
+        alphap = alphap * D2LIM / D2ABS;
+    } else {
+        if (bigp) {
+            double sgn = copysign(1.0, alpham);
+            double amax = -alphap * alphap / (4.0 * (alpham + alphap));
+            double delam = sm1 - s0;
+            if (sgn * amax >= sgn * delam) {
+                if (sgn * (delam - alpham) >= 1.e-10) {
+                    alphap = (-2.0 * delam - 2.0 * sgn * sqrt(delam * delam - delam * alpham));
+                } else {
+                    alphap = -2.0 * alpham;
+                }
+            }
+        }
+        if (bigm) {
+            double sgn = copysign(1.0, alphap);
+            double amax = -alpham * alpham / (4.0 * (alpham + alphap));
+            double delap = sp1 - s0;
+            if (sgn * amax >= sgn * delap) {
+                if (sgn * (delap - alphap) >= bigm_thresh) {
+                    alpham = (-2.0 * delap - 2.0 * sgn * sqrt(delap * delap - delap * alphap));
+                } else {
+                    alpham = -2.0 * alphap;
+                }
+            }
+        }
+    }
+    *sm_out = s0 + alpham;
+    *sp_out = s0 + alphap;
+}
+
+static void ppm_dir(const Ctx* c, int d, const CView* s, const CView* vel, Tmp* Ip, Tmp* Im,
+                    int bclo, int bchi) {
+    const int e0 = d == 0, e1 = d == 1, e2 = d == 2;
+    const int lo = c->domlo[d], hi = c->domhi[d];
+    const int lobc = (bclo == BC_EXT_DIR || bclo == BC_HOEXTRAP);
+    const int hibc = (bchi == BC_EXT_DIR || bchi == BC_HOEXTRAP);
+    const double dt = c->dt, h = c->dx[d], eps = c->rel_eps;
+    for (int k = c->obx.lo[2]; k <= c->obx.hi[2]; ++k)
+    for (int j = c->obx.lo[1]; j <= c->obx.hi[1]; ++j)
+    for (int i = c->obx.lo[0]; i <= c->obx.hi[0]; ++i) {
+#define S(o) RD(*s, i + (o) * e0, j + (o) * e1, k + (o) * e2)
+        const int I = d == 0 ? i : (d == 1 ? j : k);
+        double sm, sp;
+        const double s0 = S(0);
+        if (c->ppm_type == 1) {
+            /* MaestroPPM.cpp:34-205 */
+            double dl = vanleer(S(-2), S(-1), S(0));
+            double dc = vanleer(S(-1), S(0), S(1));
+            double dr = vanleer(S(0), S(1), S(2));
+            sm = 0.5 * (S(0) + S(-1)) - (dc - dl) / 6.0;
+            sm = dmax(sm, dmin(S(0), S(-1)));
+            sm = dmin(sm, dmax(S(0), S(-1)));
+            sp = 0.5 * (S(1) + S(0)) - (dr - dc) / 6.0;
+            sp = dmax(sp, dmin(S(1), S(0)));
+            sp = dmin(sp, dmax(S(1), S(0)));
+            const double sedgel = sp, sedger = sm;
+            cw_limit(s0, &sm, &sp);
+            if (I == lo) {
+                if (lobc) {
+                    sm = S(-1);
+                    sp = bc_edge(S(-1), S(0), S(1), S(2), S(1), S(0));
+                }
+            } else if (I == lo + 1) {
+                if (lobc) {
+                    sm = bc_edge(S(-2), S(-1), S(0), S(1), S(0), S(-1));
+                    sp = sedgel;
+                    cw_limit(s0, &sm, &sp);
+                }
+            } else if (I == hi) {
+                if (hibc) {
+                    sp = S(1);
+                    sm = bc_edge(S(1), S(0), S(-1), S(-2), S(-1), S(0));
+                }
+            } else if (I == hi - 1) {
+                if (hibc) {
+                    sp = bc_edge(S(2), S(1), S(0), S(-1), S(0), S(1));
+                    sm = sedger;
+                    cw_limit(s0, &sm, &sp);
+                }
+            }
+        } else {
+            /* ppm_type == 2, MaestroPPM.cpp:255-719 */
+            double sedgel = cs_edge(S(-3), S(-2), S(-1), S(0));
+            double sedge = cs_edge(S(-2), S(-1), S(0), S(1));
+            double sedger = cs_edge(S(-1), S(0), S(1), S(2));
+            double sedgerr = cs_edge(S(0), S(1), S(2), S(3));
+            cs_limit(sedgel, sedge, sedger, sedgerr, S(-2), S(-1), S(0), S(1), S(2), 1.e-10,
+                     &sm, &sp);
+            if (lobc) {
+                if (I == lo) {
+                    sm = S(-1);
+                    sp = bc_edge(S(-1), S(0), S(1), S(2), S(1), S(0));
+                } else if (I == lo + 1) {
+                    sedgel = S(-2);
+                    sedge = bc_edge(S(-2), S(-1), S(0), S(1), S(0), S(-1));
+                } else if (I == lo + 2) {
+                    sedgel = bc_edge(S(-3), S(-2), S(-1), S(0), S(-1), S(-2));
+                }
+                if (I == lo + 1 || I == lo + 2) {
+                    /* QUIRK: the x-direction lo-side re-application tests `>= 1.e10` in the
+                     * bigm branch (MaestroPPM.cpp:566); y and z test 1.e-10 (:1300, :2044) */
+                    cs_limit(sedgel, sedge, sedger, sedgerr, S(-2), S(-1), S(0), S(1), S(2),
+                             d == 0 ? 1.e10 : 1.e-10, &sm, &sp);
+                }
+            }
+            if (hibc) {
+                if (I == hi) {
+                    sp = S(1);
+                    sm = bc_edge(S(1), S(0), S(-1), S(-2), S(-1), S(0));
+                } else if (I == hi - 1) {
+                    /* QUIRK: y and z set sedgerr = s(+2) here (MaestroPPM.cpp:1343, :2087);
+                     * the x block (:598-608) does not */
+                    if (d != 0) sedgerr = S(2);
+                    sedger = bc_edge(S(2), S(1), S(0), S(-1), S(0), S(1));
+                } else if (I == hi - 2) {
+                    sedgerr = bc_edge(S(3), S(2), S(1), S(0), S(1), S(2));
+                }
+                if (I == hi - 1 || I == hi - 2) {
+                    cs_limit(sedgel, sedge, sedger, sedgerr, S(-2), S(-1), S(0), S(1), S(2),
+                             1.e-10, &sm, &sp);
+                }
+            }
+        }
+        /* MaestroPPM.cpp:210-231 (is_umac) */
+        const double s6 = 6.0 * s0 - 3.0 * (sm + sp);
+        const double up = RD(*vel, i + e0, j + e1, k + e2);
+        const double um = RD(*vel, i, j, k);
+        double sigma = fabs(up) * dt / h;
+        if (up > eps) {
+            T(*Ip, i, j, k) = sp - 0.5 * sigma * (sp - sm - (1.0 - 2.0 / 3.0 * sigma) * s6);
+        } else {
+            T(*Ip, i, j, k) = s0;
+        }
+        sigma = fabs(um) * dt / h;
+        if (um < -eps) {
+            T(*Im, i, j, k) = sm + 0.5 * sigma * (sp - sm + (1.0 - 2.0 / 3.0 * sigma) * s6);
+        } else {
+            T(*Im, i, j, k) = s0;
+        }
+#undef S
+    }
+}
+
+/* physical-BC override of a left/right pair at a domain face; the pattern shared by
+ * MaestroMakeEdgeScalars.cpp:710-742 (predictor) and :933-965 etc. (transverse) */
+static inline void bc_pair(int I, int lo, int hi, int bclo, int bchi, int velclamp,
+                           double s_lo_ghost, double s_hi_ghost, double* sl, double* sr) {
+    if (I == lo) {
+        if (bclo == BC_EXT_DIR) {
+            *sl = s_lo_ghost;
+            *sr = s_lo_ghost;
+        } else if (bclo == BC_FOEXTRAP || bclo == BC_HOEXTRAP) {
+            if (velclamp) *sr = dmin(*sr, 0.0);
+            *sl = *sr;
+        } else if (bclo == BC_REFLECT_EVEN) {
+            *sl = *sr;
+        } else if (bclo == BC_REFLECT_ODD) {
+            *sl = 0.0;
+            *sr = 0.0;
+        }
+    } else if (I == hi + 1) {
+        if (bchi == BC_EXT_DIR) {
+            *sl = s_hi_ghost;
+            *sr = s_hi_ghost;
+        } else if (bchi == BC_FOEXTRAP || bchi == BC_HOEXTRAP) {
+            if (velclamp) *sl = dmax(*sl, 0.0);
+            *sr = *sl;
+        } else if (bchi == BC_REFLECT_EVEN) {
+            *sr = *sl;
+        } else if (bchi == BC_REFLECT_ODD) {
+            *sl = 0.0;
+            *sr = 0.0;
+        }
+    }
+}
+
+static inline double upwind(double u, double eps, double sl, double sr) {
+    double r = (u > 0.0) ? sl : sr;
+    return (fabs(u) > eps) ? r : 0.5 * (sl + sr);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* MakeEdgeScalPredictor: 3-D MaestroMakeEdgeScalars.cpp:662-863, 2-D :306-452           */
+/* faces of direction d: index d in [vlo, vhi+1], other directions in [vlo-1, vhi+1]      */
+/* ------------------------------------------------------------------------------------ */
+static void predictor_dir(const Ctx* c, int d, const CView* s, const CView* vel,
+                          const Tmp* Ip_or_slope, const Tmp* Im, Tmp* sl, Tmp* sr, Tmp* simh,
+                          int bclo, int bchi, int comp) {
+    const int e0 = d == 0, e1 = d == 1, e2 = d == 2;
+    IBox b = c->obx;
+    b.lo[d] += 1;
+    const double h = c->dx[d], dt = c->dt, dt2 = 0.5 * c->dt;
+    /* QUIRK: the 3-D predictor upwinds with |u| > 0.0 (MaestroMakeEdgeScalars.cpp:746,803,
+     * 859); the 2-D one with rel_eps (:389,448) */
+    const double eps = (c->dim == 3) ? 0.0 : c->rel_eps;
+    for (int k = b.lo[2]; k <= b.hi[2]; ++k)
+    for (int j = b.lo[1]; j <= b.hi[1]; ++j)
+    for (int i = b.lo[0]; i <= b.hi[0]; ++i) {
+        const int I = d == 0 ? i : (d == 1 ? j : k);
+        const double u = RD(*vel, i, j, k);
+        const double sL = RD(*s, i - e0, j - e1, k - e2), sR = RD(*s, i, j, k);
+        double l, r;
+        if (c->ppm_type == 0) {
+            const double slpL = T(*Ip_or_slope, i - e0, j - e1, k - e2);
+            const double slpR = T(*Ip_or_slope, i, j, k);
+            if (c->dim == 3) {
+                /* :698-703 */
+                l = sL + 0.5 * (1.0 - dt * u / h) * slpL;
+                r = sR - 0.5 * (1.0 + dt * u / h) * slpR;
+            } else {
+                /* QUIRK: 2-D association differs (:341-345) */
+                l = sL + (0.5 - dt2 * u / h) * slpL;
+                r = sR - (0.5 + dt2 * u / h) * slpR;
+            }
+        } else {
+            l = T(*Ip_or_slope, i - e0, j - e1, k - e2);
+            r = T(*Im, i, j, k);
+        }
+        bc_pair(I, c->domlo[d], c->domhi[d], bclo, bchi, c->is_vel && comp == d, sL, sR, &l,
+                &r);
+        T(*sl, i, j, k) = l;
+        T(*sr, i, j, k) = r;
+        T(*simh, i, j, k) = upwind(u, eps, l, r);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* MakeEdgeScalTransverse (3-D): MaestroMakeEdgeScalars.cpp:865-1359.  simh_{d|t}: state  */
+/* on d-faces corrected by the t-direction transverse term; the box is the valid box with */
+/* the d-faces [vlo, vhi+1] and grown by one in the third direction o (:897-898 etc.).    */
+/* ------------------------------------------------------------------------------------ */
+static void transverse(const Ctx* c, int d, int t, const CView* s, const CView* vel_d,
+                       const CView* vel_t, const Tmp* sl, const Tmp* sr, const Tmp* simh_t,
+                       const Tmp* divu, Tmp* out, int bclo, int bchi, int comp) {
+    const int o = 3 - d - t;
+    const int e[3] = {d == 0, d == 1, d == 2};
+    const int f[3] = {t == 0, t == 1, t == 2};
+    IBox b = c->valid;
+    b.lo[o] -= 1;
+    b.hi[o] += 1;
+    b.hi[d] += 1;
+    const double dt3 = c->dt / 3.0, dt6 = c->dt / 6.0, ht = c->dx[t];
+    for (int k = b.lo[2]; k <= b.hi[2]; ++k)
+    for (int j = b.lo[1]; j <= b.hi[1]; ++j)
+    for (int i = b.lo[0]; i <= b.hi[0]; ++i) {
+        const int I = d == 0 ? i : (d == 1 ? j : k);
+        /* left cell L = (i,j,k) - e_d, right cell R = (i,j,k) */
+        const int li = i - e[0], lj = j - e[1], lk = k - e[2];
+        double l, r;
+        const double sL = RD(*s, li, lj, lk), sR = RD(*s, i, j, k);
+        if (c->is_cons) {
+            /* :909-921 */
+            l = T(*sl, i, j, k) -
+                (dt3 / ht) * (T(*simh_t, li + f[0], lj + f[1], lk + f[2]) *
+                                  RD(*vel_t, li + f[0], lj + f[1], lk + f[2]) -
+                              T(*simh_t, li, lj, lk) * RD(*vel_t, li, lj, lk)) -
+                dt3 * sL * T(*divu, li, lj, lk) +
+                (dt3 / ht) * sL *
+                    (RD(*vel_t, li + f[0], lj + f[1], lk + f[2]) - RD(*vel_t, li, lj, lk));
+            r = T(*sr, i, j, k) -
+                (dt3 / ht) * (T(*simh_t, i + f[0], j + f[1], k + f[2]) *
+                                  RD(*vel_t, i + f[0], j + f[1], k + f[2]) -
+                              T(*simh_t, i, j, k) * RD(*vel_t, i, j, k)) -
+                dt3 * sR * T(*divu, i, j, k) +
+                (dt3 / ht) * sR *
+                    (RD(*vel_t, i + f[0], j + f[1], k + f[2]) - RD(*vel_t, i, j, k));
+        } else {
+            /* :924-929 */
+            l = T(*sl, i, j, k) -
+                (dt6 / ht) *
+                    (RD(*vel_t, li + f[0], lj + f[1], lk + f[2]) + RD(*vel_t, li, lj, lk)) *
+                    (T(*simh_t, li + f[0], lj + f[1], lk + f[2]) - T(*simh_t, li, lj, lk));
+            r = T(*sr, i, j, k) -
+                (dt6 / ht) *
+                    (RD(*vel_t, i + f[0], j + f[1], k + f[2]) + RD(*vel_t, i, j, k)) *
+                    (T(*simh_t, i + f[0], j + f[1], k + f[2]) - T(*simh_t, i, j, k));
+        }
+        bc_pair(I, c->domlo[d], c->domhi[d], bclo, bchi, c->is_vel && comp == d, sL, sR, &l,
+                &r);
+        T(*out, i, j, k) = upwind(RD(*vel_d, i, j, k), c->rel_eps, l, r);
+    }
+}
+
+/* final physical-BC override of the edge state, MaestroMakeEdgeScalars.cpp:1455-1485 */
+static inline double bc_final(int I, int lo, int hi, int bclo, int bchi, int velclamp,
+                              double s_lo_ghost, double s_hi_ghost, double el, double er,
+                              double val) {
+    if (I == lo) {
+        if (bclo == BC_EXT_DIR) {
+            val = s_lo_ghost;
+        } else if (bclo == BC_FOEXTRAP || bclo == BC_HOEXTRAP) {
+            val = velclamp ? dmin(er, 0.0) : er;
+        } else if (bclo == BC_REFLECT_EVEN) {
+            val = er;
+        } else if (bclo == BC_REFLECT_ODD) {
+            val = 0.0;
+        }
+    } else if (I == hi + 1) {
+        if (bchi == BC_EXT_DIR) {
+            val = s_hi_ghost;
+        } else if (bchi == BC_FOEXTRAP || bchi == BC_HOEXTRAP) {
+            val = velclamp ? dmax(el, 0.0) : el;
+        } else if (bchi == BC_REFLECT_EVEN) {
+            val = el;
+        } else if (bchi == BC_REFLECT_ODD) {
+            val = 0.0;
+        }
+    }
+    return val;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* MakeEdgeScalEdges: 3-D MaestroMakeEdgeScalars.cpp:1361-1667, 2-D :454-644.             */
+/* tr1/tr2: the transverse states for the two other directions t1 < t2 (3-D: simh_{t1|t2} */
+/* and simh_{t2|t1}; 2-D: simh_{t1} only).                                                */
+/* ------------------------------------------------------------------------------------ */
+static void edges_dir(const Ctx* c, int d, const CView* s, const CView* vel[3],
+                      const CView* force, const Tmp* Ipf, const Tmp* Imf, const Tmp* sl,
+                      const Tmp* sr, const Tmp* tr1, const Tmp* tr2, int t1, int t2,
+                      const MxFab* sedge, int comp, int bclo, int bchi) {
+    const int e[3] = {d == 0, d == 1, d == 2};
+    const int f1[3] = {t1 == 0, t1 == 1, t1 == 2};
+    const int f2[3] = {t2 == 0, t2 == 1, t2 == 2};
+    IBox b = c->valid;
+    b.hi[d] += 1;
+    const double dt2 = 0.5 * c->dt, dt4 = 0.25 * c->dt;
+    const double hd = c->dx[d], h1 = c->dx[t1], h2 = (c->dim == 3) ? c->dx[t2] : 0.0;
+    const long nx = sedge->hi[0] - sedge->lo[0] + 1, ny = sedge->hi[1] - sedge->lo[1] + 1,
+               nz = sedge->hi[2] - sedge->lo[2] + 1;
+    double* out = sedge->p + (long)comp * nx * ny * nz;
+    const CView* vd = vel[d];
+    const CView* v1 = vel[t1];
+    const CView* v2 = (c->dim == 3) ? vel[t2] : NULL;
+    for (int k = b.lo[2]; k <= b.hi[2]; ++k)
+    for (int j = b.lo[1]; j <= b.hi[1]; ++j)
+    for (int i = b.lo[0]; i <= b.hi[0]; ++i) {
+        const int I = d == 0 ? i : (d == 1 ? j : k);
+        const int li = i - e[0], lj = j - e[1], lk = k - e[2];
+        const double sL = RD(*s, li, lj, lk), sR = RD(*s, i, j, k);
+        const double fl = (c->ppm_trace_forces == 0) ? RD(*force, li, lj, lk) : T(*Ipf, li, lj, lk);
+        const double fr = (c->ppm_trace_forces == 0) ? RD(*force, i, j, k) : T(*Imf, i, j, k);
+        double el, er;
+#define P1(q, a, b_, c_) q(a + f1[0], b_ + f1[1], c_ + f1[2])
+#define V1(a, b_, c_) RD(*v1, a, b_, c_)
+#define V2(a, b_, c_) RD(*v2, a, b_, c_)
+#define VD(a, b_, c_) RD(*vd, a, b_, c_)
+#define TR1(a, b_, c_) T(*tr1, a, b_, c_)
+#define TR2(a, b_, c_) T(*tr2, a, b_, c_)
+        if (c->dim == 3) {
+            if (c->is_cons) {
+                /* :1412-1429 */
+                el = T(*sl, i, j, k) -
+                     (dt2 / h1) * (TR1(li + f1[0], lj + f1[1], lk + f1[2]) *
+                                       V1(li + f1[0], lj + f1[1], lk + f1[2]) -
+                                   TR1(li, lj, lk) * V1(li, lj, lk)) -
+                     (dt2 / h2) * (TR2(li + f2[0], lj + f2[1], lk + f2[2]) *
+                                       V2(li + f2[0], lj + f2[1], lk + f2[2]) -
+                                   TR2(li, lj, lk) * V2(li, lj, lk)) -
+                     (dt2 / hd) * sL * (VD(i, j, k) - VD(li, lj, lk)) + dt2 * fl;
+                er = T(*sr, i, j, k) -
+                     (dt2 / h1) * (TR1(i + f1[0], j + f1[1], k + f1[2]) *
+                                       V1(i + f1[0], j + f1[1], k + f1[2]) -
+                                   TR1(i, j, k) * V1(i, j, k)) -
+                     (dt2 / h2) * (TR2(i + f2[0], j + f2[1], k + f2[2]) *
+                                       V2(i + f2[0], j + f2[1], k + f2[2]) -
+                                   TR2(i, j, k) * V2(i, j, k)) -
+                     (dt2 / hd) * sR * (VD(i + e[0], j + e[1], k + e[2]) - VD(i, j, k)) +
+                     dt2 * fr;
+            } else {
+                /* :1431-1443 */
+                el = T(*sl, i, j, k) -
+                     (dt4 / h1) *
+                         (V1(li + f1[0], lj + f1[1], lk + f1[2]) + V1(li, lj, lk)) *
+                         (TR1(li + f1[0], lj + f1[1], lk + f1[2]) - TR1(li, lj, lk)) -
+                     (dt4 / h2) *
+                         (V2(li + f2[0], lj + f2[1], lk + f2[2]) + V2(li, lj, lk)) *
+                         (TR2(li + f2[0], lj + f2[1], lk + f2[2]) - TR2(li, lj, lk)) +
+                     dt2 * fl;
+                er = T(*sr, i, j, k) -
+                     (dt4 / h1) * (V1(i + f1[0], j + f1[1], k + f1[2]) + V1(i, j, k)) *
+                         (TR1(i + f1[0], j + f1[1], k + f1[2]) - TR1(i, j, k)) -
+                     (dt4 / h2) * (V2(i + f2[0], j + f2[1], k + f2[2]) + V2(i, j, k)) *
+                         (TR2(i + f2[0], j + f2[1], k + f2[2]) - TR2(i, j, k)) +
+                     dt2 * fr;
+            }
+        } else {
+            if (c->is_cons) {
+                /* :499-511 */
+                el = T(*sl, i, j, k) -
+                     (dt2 / h1) * (TR1(li + f1[0], lj + f1[1], lk + f1[2]) *
+                                       V1(li + f1[0], lj + f1[1], lk + f1[2]) -
+                                   TR1(li, lj, lk) * V1(li, lj, lk)) -
+                     (dt2 / hd) * sL * (VD(i, j, k) - VD(li, lj, lk)) + dt2 * fl;
+                er = T(*sr, i, j, k) -
+                     (dt2 / h1) * (TR1(i + f1[0], j + f1[1], k + f1[2]) *
+                                       V1(i + f1[0], j + f1[1], k + f1[2]) -
+                                   TR1(i, j, k) * V1(i, j, k)) -
+                     (dt2 / hd) * sR * (VD(i + e[0], j + e[1], k + e[2]) - VD(i, j, k)) +
+                     dt2 * fr;
+            } else {
+                /* :513-520 */
+                el = T(*sl, i, j, k) -
+                     (dt4 / h1) *
+                         (V1(li + f1[0], lj + f1[1], lk + f1[2]) + V1(li, lj, lk)) *
+                         (TR1(li + f1[0], lj + f1[1], lk + f1[2]) - TR1(li, lj, lk)) +
+                     dt2 * fl;
+                er = T(*sr, i, j, k) -
+                     (dt4 / h1) * (V1(i + f1[0], j + f1[1], k + f1[2]) + V1(i, j, k)) *
+                         (TR1(i + f1[0], j + f1[1], k + f1[2]) - TR1(i, j, k)) +
+                     dt2 * fr;
+            }
+        }
+#undef P1
+#undef V1
+#undef V2
+#undef VD
+#undef TR1
+#undef TR2
+        double val = upwind(RD(*vd, i, j, k), c->rel_eps, el, er);
+        val = bc_final(I, c->domlo[d], c->domhi[d], bclo, bchi, c->is_vel && comp == d, sL, sR,
+                       el, er, val);
+        out[(i - sedge->lo[0]) + nx * ((j - sedge->lo[1]) + ny * (long)(k - sedge->lo[2]))] = val;
+    }
+}
+
+static void fill_ctx(Ctx* c, const MxGeom* g, const MxEdgeParams* p) {
+    memset(c, 0, sizeof(*c));
+    c->dim = g->dim;
+    for (int d = 0; d < 3; ++d) {
+        c->valid.lo[d] = d < g->dim ? g->valid_lo[d] : 0;
+        c->valid.hi[d] = d < g->dim ? g->valid_hi[d] : 0;
+        c->domlo[d] = d < g->dim ? g->dom_lo[d] : 0;
+        c->domhi[d] = d < g->dim ? g->dom_hi[d] : 0;
+        c->dx[d] = d < g->dim ? g->dx[d] : 0.0;
+    }
+    c->obx = grow_all(c->valid, 1, g->dim);
+    c->dt = p->dt;
+    c->rel_eps = p->rel_eps;
+    c->ppm_type = p->ppm_type;
+    c->slope_order = p->slope_order;
+    c->ppm_trace_forces = p->ppm_trace_forces;
+    c->is_vel = p->is_vel;
+    c->is_cons = p->is_conservative;
+}
+
+/* Maestro::MakeEdgeScal, Source/MaestroMakeEdgeScalars.cpp:6-302 (one box, one level) */
+int orc_make_edge_scal(const MxGeom* g, const MxFab* state, const MxFab* sedge,
+                       const MxFab* umac, const MxFab* force, const MxEdgeParams* p) {
+    Ctx c;
+    fill_ctx(&c, g, p);
+    const int dim = g->dim;
+    CView vel[3];
+    const CView* velp[3] = {&vel[0], &vel[1], &vel[2]};
+    for (int d = 0; d < dim; ++d) vel[d] = cview(&umac[d], 0);
+
+    Tmp Ip[3], Im[3], Ipf[3], Imf[3], sl[3], sr[3], simh[3], tr[3][3], divu;
+    for (int d = 0; d < dim; ++d) {
+        Ip[d] = tmp_alloc(c.obx); Im[d] = tmp_alloc(c.obx);
+        Ipf[d] = tmp_alloc(c.obx); Imf[d] = tmp_alloc(c.obx);
+        sl[d] = tmp_alloc(c.obx); sr[d] = tmp_alloc(c.obx); simh[d] = tmp_alloc(c.obx);
+        for (int t = 0; t < dim; ++t) tr[d][t] = tmp_alloc(c.obx);
+    }
+    divu = tmp_alloc(c.obx);
+
+    if (dim == 3 && c.is_cons) {
+        /* MakeDivU, :648-660.  QUIRK: the whole sum is divided by dx[0] (:658) */
+        for (int k = c.obx.lo[2]; k <= c.obx.hi[2]; ++k)
+        for (int j = c.obx.lo[1]; j <= c.obx.hi[1]; ++j)
+        for (int i = c.obx.lo[0]; i <= c.obx.hi[0]; ++i) {
+            double v = RD(vel[0], i + 1, j, k) - RD(vel[0], i, j, k) + RD(vel[1], i, j + 1, k) -
+                       RD(vel[1], i, j, k) + RD(vel[2], i, j, k + 1) - RD(vel[2], i, j, k);
+            v /= c.dx[0];
+            T(divu, i, j, k) = v;
+        }
+    }
+
+    for (int n = 0; n < p->num_comp; ++n) {
+        const int comp = p->start_scomp + n;
+        const int bccomp = p->start_bccomp + n;
+        const int* bc = p->bc + 6 * bccomp;
+        const CView s = cview(state, comp);
+        const CView fv = cview(force, comp);
+        for (int d = 0; d < dim; ++d) {
+            if (c.ppm_type == 0) {
+                slope_dir(&c, d, &s, &Ip[d], bc[d], bc[3 + d]); /* :207-216 */
+            } else {
+                ppm_dir(&c, d, &s, &vel[d], &Ip[d], &Im[d], bc[d], bc[3 + d]); /* :219-221 */
+                if (c.ppm_trace_forces == 1) {
+                    ppm_dir(&c, d, &fv, &vel[d], &Ipf[d], &Imf[d], bc[d], bc[3 + d]);
+                }
+            }
+        }
+        for (int d = 0; d < dim; ++d) {
+            predictor_dir(&c, d, &s, &vel[d], &Ip[d], &Im[d], &sl[d], &sr[d], &simh[d], bc[d],
+                          bc[3 + d], comp);
+        }
+        if (dim == 3) {
+            for (int d = 0; d < 3; ++d)
+                for (int t = 0; t < 3; ++t)
+                    if (t != d)
+                        transverse(&c, d, t, &s, &vel[d], &vel[t], &sl[d], &sr[d], &simh[t],
+                                   &divu, &tr[d][t], bc[d], bc[3 + d], comp);
+            for (int d = 0; d < 3; ++d) {
+                const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+                /* sedge_d uses simh_{t1|t2} and simh_{t2|t1} (:1414-1417 etc.) */
+                edges_dir(&c, d, &s, velp, &fv, &Ipf[d], &Imf[d], &sl[d], &sr[d], &tr[t1][t2],
+                          &tr[t2][t1], t1, t2, &sedge[d], comp, bc[d], bc[3 + d]);
+            }
+        } else {
+            for (int d = 0; d < 2; ++d) {
+                const int t1 = 1 - d;
+                edges_dir(&c, d, &s, velp, &fv, &Ipf[d], &Imf[d], &sl[d], &sr[d], &simh[t1],
+                          NULL, t1, t1, &sedge[d], comp, bc[d], bc[3 + d]);
+            }
+        }
+    }
+
+    for (int d = 0; d < dim; ++d) {
+        free(Ip[d].p); free(Im[d].p); free(Ipf[d].p); free(Imf[d].p);
+        free(sl[d].p); free(sr[d].p); free(simh[d].p);
+        for (int t = 0; t < dim; ++t) free(tr[d][t].p);
+    }
+    free(divu.p);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* fluxes                                                                                */
+/* ------------------------------------------------------------------------------------ */
+static inline double* fab_at(const MxFab* f, int i, int j, int k, int n) {
+    const long nx = f->hi[0] - f->lo[0] + 1, ny = f->hi[1] - f->lo[1] + 1,
+               nz = f->hi[2] - f->lo[2] + 1;
+    return f->p + (i - f->lo[0]) + nx * ((j - f->lo[1]) + ny * ((k - f->lo[2]) + nz * (long)n));
+}
+static inline double base_at(const MxBase* b, int lev, int r) {
+    return b->p[(lev * b->len + r) * b->nvar];
+}
+
+/* Maestro::MakeRhoXFlux, Source/MaestroMakeFlux.cpp:18-465 (one box) */
+int orc_make_rhoX_flux(const MxGeom* g, const MxFab* sflux, const MxFab* etarhoflux,
+                       const MxFab* sedge, const MxFab* umac, const MxBase* rho0_old,
+                       const MxBase* rho0_edge_old, const MxFab* r0mac_old,
+                       const MxBase* rho0_new, const MxBase* rho0_edge_new,
+                       const MxFab* r0mac_new, const MxBase* rho0_predicted_edge,
+                       const MxBase* w0, const MxFluxParams* p) {
+    const int dim = g->dim, lev = p->lev, vert = dim - 1;
+    for (int d = 0; d < dim; ++d) {
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int q = 0; q < dim; ++q) { lo[q] = g->valid_lo[q]; hi[q] = g->valid_hi[q]; }
+        hi[d] += 1;
+        for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+            const int r = (dim == 3) ? k : j; /* radial index of this face / cell */
+            double* frho = fab_at(&sflux[d], i, j, k, p->rho_comp);
+            *frho = 0.0; /* :47-51 */
+            const double u = *fab_at((MxFab*)&umac[d], i, j, k, 0);
+            for (int comp = p->start_comp; comp < p->start_comp + p->num_comp; ++comp) {
+                double rho0_edge;
+                if (dim == 3 && p->spherical) {
+                    /* :65-70 LinComb, then :326-329 */
+                    rho0_edge = 0.5 * *fab_at((MxFab*)&r0mac_old[d], i, j, k, 0) +
+                                0.5 * *fab_at((MxFab*)&r0mac_new[d], i, j, k, 0);
+                } else if (d == vert) {
+                    rho0_edge = 0.5 * (base_at(rho0_edge_old, lev, r) + base_at(rho0_edge_new, lev, r));
+                } else {
+                    rho0_edge = 0.5 * (base_at(rho0_old, lev, r) + base_at(rho0_new, lev, r));
+                }
+                double* F = fab_at(&sflux[d], i, j, k, comp);
+                const double se = *fab_at((MxFab*)&sedge[d], i, j, k, comp);
+                const double ser = *fab_at((MxFab*)&sedge[d], i, j, k, p->rho_comp);
+                if (p->species_pred_type == MX_PRED_RHOPRIME_AND_X) {
+                    *F = u * (rho0_edge + ser) * se;
+                } else if (p->species_pred_type == MX_PRED_RHOX) {
+                    *F = u * se;
+                } else if (p->species_pred_type == MX_PRED_RHO_AND_X) {
+                    *F = u * ser * se;
+                }
+                if (d == vert && !(dim == 3 && p->spherical)) {
+                    /* :288-301 */
+                    if (p->evolve_base_state && !p->use_exact_base_state) {
+                        double* eta = fab_at((MxFab*)etarhoflux, i, j, k, 0);
+                        if (comp >= p->first_spec && comp <= p->first_spec + p->num_spec - 1) {
+                            *eta += *F;
+                        }
+                        if (comp == p->first_spec + p->num_spec - 1) {
+                            *eta -= base_at(w0, lev, r) * base_at(rho0_predicted_edge, lev, r);
+                        }
+                    }
+                }
+                *frho += *F; /* :223 */
+            }
+        }
+    }
+    return 0;
+}
+
+/* Maestro::MakeRhoHFlux, Source/MaestroMakeFlux.cpp:467-1067 (one box) */
+int orc_make_rhoh_flux(const MxGeom* g, const MxFab* sflux, const MxFab* sedge,
+                       const MxFab* umac, const MxBase* rho0_old, const MxBase* rho0_edge_old,
+                       const MxFab* r0mac_old, const MxBase* rho0_new,
+                       const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                       const MxBase* rhoh0_old, const MxBase* rhoh0_edge_old,
+                       const MxFab* rh0mac_old, const MxBase* rhoh0_new,
+                       const MxBase* rhoh0_edge_new, const MxFab* rh0mac_new,
+                       const MxFab* h0mac_old, const MxFab* h0mac_new, const MxFluxParams* p) {
+    const int dim = g->dim, lev = p->lev, vert = dim - 1;
+    const int ept = p->enthalpy_pred_type, spt = p->species_pred_type;
+    const int have_h = ept == MX_PRED_H || ept == MX_PRED_T_THEN_H || ept == MX_PRED_TPRIME_THEN_H;
+    const int have_hprime = ept == MX_PRED_HPRIME;
+    const int have_rhoh = ept == MX_PRED_RHOH;
+    const int RhoC = p->rho_comp, RhoHC = p->rhoh_comp;
+    for (int d = 0; d < dim; ++d) {
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int q = 0; q < dim; ++q) { lo[q] = g->valid_lo[q]; hi[q] = g->valid_hi[q]; }
+        hi[d] += 1;
+        for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+            const int r = (dim == 3) ? k : j;
+            double* F = fab_at(&sflux[d], i, j, k, RhoHC);
+            const double u = *fab_at((MxFab*)&umac[d], i, j, k, 0);
+            const double seh = *fab_at((MxFab*)&sedge[d], i, j, k, RhoHC);
+            const double ser = *fab_at((MxFab*)&sedge[d], i, j, k, RhoC);
+            if (!(dim == 3 && p->spherical)) {
+                /* planar: 2-D :600-669, 3-D :674-786 */
+                if (have_h) {
+                    if (spt == MX_PRED_RHOPRIME_AND_X) {
+                        double rho0_edge =
+                            (d == vert)
+                                ? 0.5 * (base_at(rho0_edge_old, lev, r) + base_at(rho0_edge_new, lev, r))
+                                : 0.5 * (base_at(rho0_old, lev, r) + base_at(rho0_new, lev, r));
+                        *F = u * (rho0_edge + ser) * seh;
+                    } else if (spt == MX_PRED_RHO_AND_X || spt == MX_PRED_RHOX) {
+                        *F = u * ser * seh;
+                    }
+                } else if (have_rhoh) {
+                    *F = u * seh;
+                } else if (ept == MX_PRED_RHOHPRIME || ept == MX_PRED_T_THEN_RHOHPRIME) {
+                    if (d == vert) {
+                        double rhoh0_edge = 0.5 * (base_at(rhoh0_edge_old, lev, r) +
+                                                   base_at(rhoh0_edge_new, lev, r));
+                        *F = u * (seh + rhoh0_edge); /* :782-784 */
+                    } else {
+                        double rhoh0_edge =
+                            0.5 * (base_at(rhoh0_old, lev, r) + base_at(rhoh0_new, lev, r));
+                        *F = u * (rhoh0_edge + seh); /* :706-708 */
+                    }
+                }
+            } else if (p->use_exact_base_state) {
+                /* spherical, exact base state :788-858 */
+                /* QUIRK: the x-face test is `have_h || have_rhoh` (:797), so predict_rhoh
+                 * leaves the x-flux untouched; y and z test `have_h || have_hprime` */
+                const int skip = (d == 0) ? (have_h || have_rhoh) : (have_h || have_hprime);
+                if (skip) {
+                } else if (have_rhoh) {
+                    *F = u * seh;
+                } else {
+                    double rhoh0_edge = 0.5 * *fab_at((MxFab*)&rh0mac_old[d], i, j, k, 0) +
+                                        0.5 * *fab_at((MxFab*)&rh0mac_new[d], i, j, k, 0);
+                    *F = u * (rhoh0_edge + seh);
+                }
+            } else {
+                /* spherical :860-1021 */
+                const double rho0_edge = 0.5 * *fab_at((MxFab*)&r0mac_old[d], i, j, k, 0) +
+                                         0.5 * *fab_at((MxFab*)&r0mac_new[d], i, j, k, 0);
+                const double h0_edge = 0.5 * *fab_at((MxFab*)&h0mac_old[d], i, j, k, 0) +
+                                       0.5 * *fab_at((MxFab*)&h0mac_new[d], i, j, k, 0);
+                if (have_h) {
+                    if (spt == MX_PRED_RHOPRIME_AND_X) {
+                        *F = u * (rho0_edge + ser) * seh;
+                    } else if (spt == MX_PRED_RHO_AND_X || spt == MX_PRED_RHOX) {
+                        *F = u * ser * seh;
+                    }
+                } else if (have_hprime) {
+                    if (spt == MX_PRED_RHOPRIME_AND_X) {
+                        *F = u * (ser + rho0_edge) * (seh + h0_edge);
+                    }
+                } else if (have_rhoh) {
+                    *F = u * seh;
+                } else {
+                    *F = u * (rho0_edge * h0_edge + seh);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+/* Maestro::CelltoEdge, Source/MaestroCelltoEdge.cpp:5-55; one level, one chunk [r_lo, r_hi] */
+int orc_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi) {
+    const int lo = r_lo, hi = r_hi + 1;
+    for (int r = lo; r <= hi; ++r) {
+        if (r == 0) {
+            edge[r] = cell[r];
+        } else if (r == 1 || r == lo) {
+            edge[r] = 0.5 * (cell[r - 1] + cell[r]);
+        } else if (r == nr) {
+            edge[r] = cell[r - 1];
+        } else if (r == nr - 1 || r == hi) {
+            edge[r] = 0.5 * (cell[r] + cell[r - 1]);
+        } else {
+            double tmp = 7.0 / 12.0 * (cell[r] + cell[r - 1]) - 1.0 / 12.0 * (cell[r + 1] + cell[r - 2]);
+            double s0min = dmin(cell[r], cell[r - 1]);
+            double s0max = dmax(cell[r], cell[r - 1]);
+            edge[r] = dmin(dmax(tmp, s0min), s0max);
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,260 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): extern "C" driver around the REFERENCE's own
+// Maestro::MakeEdgeScal / MakeRhoXFlux / MakeRhoHFlux / CelltoEdge, compiled from
+// /root/reference/Source/*.cpp against oracle/shim (see oracle/Makefile) into
+// oracle/_ref/libmaestro_ref{2,3}d.so.  It aliases the caller's flat arrays as single-box
+// MultiFabs and calls the reference member functions unchanged.  Used only by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs; never by
+// the product path.
+#include <Maestro.H>
+
+#include "../include/mxadv.h"
+
+using namespace amrex;
+
+// ---- definitions of the globals the shim header declares -------------------------------
+namespace maestro {
+int ppm_type = 1, slope_order = 4, ppm_trace_forces = 0, bds_type = 0;
+int species_pred_type = 1, enthalpy_pred_type = 1, reflux_type = 1;
+bool spherical = false, use_exact_base_state = false, evolve_base_state = true,
+     average_base_state = false;
+}  // namespace maestro
+int Rho = 0, RhoH = 1, Temp = 2, Pi = 3, FirstSpec = 4, NumSpec = 3, Nscal = 7;
+
+#if (AMREX_SPACEDIM == 2)
+IntVect Maestro::nodal_flag_x(1, 0);
+IntVect Maestro::nodal_flag_y(0, 1);
+IntVect Maestro::nodal_flag_z(0, 0);
+#else
+IntVect Maestro::nodal_flag_x(1, 0, 0);
+IntVect Maestro::nodal_flag_y(0, 1, 0);
+IntVect Maestro::nodal_flag_z(0, 0, 1);
+#endif
+
+namespace {
+
+constexpr int DIM = AMREX_SPACEDIM;
+
+IntVect iv(const int* v) {
+#if (AMREX_SPACEDIM == 2)
+    return IntVect(v[0], v[1]);
+#else
+    return IntVect(v[0], v[1], v[2]);
+#endif
+}
+
+Box valid_box(const MxGeom* g) { return Box(iv(g->valid_lo), iv(g->valid_hi)); }
+
+// alias `f` as a MultiFab whose valid box is `g`'s valid box made nodal in `nodal_dir`
+// (-1 = cell centred); the ghost width is read off the fab's low corner.
+void alias(MultiFab& mf, const MxGeom* g, const MxFab* f, int nodal_dir) {
+    Box vb = valid_box(g);
+    if (nodal_dir >= 0) vb.surroundingNodes(nodal_dir);
+    const int ng = g->valid_lo[0] - f->lo[0];
+    for (int d = 0; d < DIM; ++d) {
+        if (vb.lo[d] - f->lo[d] != ng || f->hi[d] - vb.hi[d] != ng) {
+            Abort("ref_driver: fab box is not the valid box grown uniformly");
+        }
+    }
+    mf.alias(vb, f->ncomp, ng, f->p);
+}
+
+void setup(Maestro& m, const MxGeom* g) {
+    if (g->dim != DIM) Abort("ref_driver: wrong dimensionality for this build");
+    m.finest_level = 0;
+    Box dom(iv(g->dom_lo), iv(g->dom_hi));
+    m.geom.resize(1);
+    m.geom[0] = Geometry(dom, g->dx);
+    m.grids.resize(1);
+    m.grids[0] = BoxArray(valid_box(g));
+    m.dmap.resize(1);
+    m.flux_reg_s.resize(2);
+}
+
+void fill_base(BaseState<Real>& b, const MxBase* src) {
+    if (src == nullptr || src->p == nullptr) {
+        b.define(1, 1, 1);
+        return;
+    }
+    b.define(src->nlev, src->len, src->nvar);
+    auto a = b.array();
+    for (int i = 0; i < src->nlev * src->len * src->nvar; ++i) a(i) = src->p[i];
+}
+
+void alias_faces(Vector<std::array<MultiFab, DIM>>& v, const MxGeom* g, const MxFab* f) {
+    v.resize(1);
+    if (f == nullptr) return;
+    for (int d = 0; d < DIM; ++d) alias(v[0][d], g, &f[d], d);
+}
+
+void set_flux_globals(const MxFluxParams* p) {
+    maestro::species_pred_type = p->species_pred_type;
+    maestro::enthalpy_pred_type = p->enthalpy_pred_type;
+    maestro::spherical = p->spherical != 0;
+    maestro::use_exact_base_state = p->use_exact_base_state != 0;
+    maestro::evolve_base_state = p->evolve_base_state != 0;
+    maestro::reflux_type = 1;
+    Rho = p->rho_comp;
+    RhoH = p->rhoh_comp;
+    FirstSpec = p->first_spec;
+    NumSpec = p->num_spec;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_dim(void) { return DIM; }
+
+int ref_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+// Maestro::MakeEdgeScal, Source/MaestroMakeEdgeScalars.cpp:6
+int ref_make_edge_scal(const MxGeom* g, const MxFab* state, const MxFab* sedge,
+                       const MxFab* umac, const MxFab* force, const MxEdgeParams* p) {
+    Maestro m;
+    setup(m, g);
+    m.dt = p->dt;
+    m.rel_eps = p->rel_eps;
+    maestro::ppm_type = p->ppm_type;
+    maestro::slope_order = p->slope_order;
+    maestro::ppm_trace_forces = p->ppm_trace_forces;
+    maestro::reflux_type = 1;
+
+    Vector<MultiFab> st(1), fo(1);
+    alias(st[0], g, state, -1);
+    alias(fo[0], g, force, -1);
+    Vector<std::array<MultiFab, DIM>> se, um;
+    alias_faces(se, g, sedge);
+    alias_faces(um, g, umac);
+
+    Vector<BCRec> bcs(p->nbccomp);
+    for (int n = 0; n < p->nbccomp; ++n) {
+        for (int d = 0; d < DIM; ++d) {
+            bcs[n].setLo(d, p->bc[6 * n + d]);
+            bcs[n].setHi(d, p->bc[6 * n + 3 + d]);
+        }
+    }
+    m.MakeEdgeScal(st, se, um, fo, p->is_vel != 0, bcs, p->nbccomp, p->start_scomp,
+                   p->start_bccomp, p->num_comp, p->is_conservative != 0);
+    return 0;
+}
+
+// Maestro::MakeRhoXFlux, Source/MaestroMakeFlux.cpp:18
+int ref_make_rhoX_flux(const MxGeom* g, const MxFab* sflux, const MxFab* etarhoflux,
+                       const MxFab* sedge, const MxFab* umac, const MxBase* rho0_old,
+                       const MxBase* rho0_edge_old, const MxFab* r0mac_old,
+                       const MxBase* rho0_new, const MxBase* rho0_edge_new,
+                       const MxFab* r0mac_new, const MxBase* rho0_predicted_edge,
+                       const MxBase* w0, const MxFluxParams* p) {
+    Maestro m;
+    setup(m, g);
+    set_flux_globals(p);
+    if (p->lev != 0) Abort("ref_driver: single level only");
+
+    // `state` is only used to drive the MFIter: give it the valid box, no data
+    Vector<MultiFab> st(1), eta(1);
+    st[0].define(m.grids[0], m.dmap[0], 1, 0);
+    alias(eta[0], g, etarhoflux, DIM - 1);
+    Vector<std::array<MultiFab, DIM>> sf, se, um, r0o, r0n;
+    alias_faces(sf, g, sflux);
+    alias_faces(se, g, sedge);
+    alias_faces(um, g, umac);
+    alias_faces(r0o, g, r0mac_old);
+    alias_faces(r0n, g, r0mac_new);
+
+    BaseState<Real> b_r0o, b_r0eo, b_r0n, b_r0en, b_r0pe;
+    fill_base(b_r0o, rho0_old);
+    fill_base(b_r0eo, rho0_edge_old);
+    fill_base(b_r0n, rho0_new);
+    fill_base(b_r0en, rho0_edge_new);
+    fill_base(b_r0pe, rho0_predicted_edge);
+    fill_base(m.w0, w0);
+
+    m.MakeRhoXFlux(st, sf, eta, se, um, b_r0o, b_r0eo, r0o, b_r0n, b_r0en, r0n, b_r0pe,
+                   p->start_comp, p->num_comp);
+    return 0;
+}
+
+// Maestro::MakeRhoHFlux, Source/MaestroMakeFlux.cpp:467
+int ref_make_rhoh_flux(const MxGeom* g, const MxFab* sflux, const MxFab* sedge,
+                       const MxFab* umac, const MxBase* rho0_old,
+                       const MxBase* rho0_edge_old, const MxFab* r0mac_old,
+                       const MxBase* rho0_new, const MxBase* rho0_edge_new,
+                       const MxFab* r0mac_new, const MxBase* rhoh0_old,
+                       const MxBase* rhoh0_edge_old, const MxFab* rh0mac_old,
+                       const MxBase* rhoh0_new, const MxBase* rhoh0_edge_new,
+                       const MxFab* rh0mac_new, const MxFab* h0mac_old,
+                       const MxFab* h0mac_new, const MxFluxParams* p) {
+    Maestro m;
+    setup(m, g);
+    set_flux_globals(p);
+    if (p->lev != 0) Abort("ref_driver: single level only");
+
+    Vector<MultiFab> st(1);
+    st[0].define(m.grids[0], m.dmap[0], 1, 0);
+    Vector<std::array<MultiFab, DIM>> sf, se, um, w0mac, r0o, r0n, rh0o, rh0n, h0o, h0n;
+    alias_faces(sf, g, sflux);
+    alias_faces(se, g, sedge);
+    alias_faces(um, g, umac);
+    w0mac.resize(1);
+    alias_faces(r0o, g, r0mac_old);
+    alias_faces(r0n, g, r0mac_new);
+    alias_faces(rh0o, g, rh0mac_old);
+    alias_faces(rh0n, g, rh0mac_new);
+    alias_faces(h0o, g, h0mac_old);
+    alias_faces(h0n, g, h0mac_new);
+
+    BaseState<Real> b_r0o, b_r0eo, b_r0n, b_r0en, b_rh0o, b_rh0eo, b_rh0n, b_rh0en;
+    fill_base(b_r0o, rho0_old);
+    fill_base(b_r0eo, rho0_edge_old);
+    fill_base(b_r0n, rho0_new);
+    fill_base(b_r0en, rho0_edge_new);
+    fill_base(b_rh0o, rhoh0_old);
+    fill_base(b_rh0eo, rhoh0_edge_old);
+    fill_base(b_rh0n, rhoh0_new);
+    fill_base(b_rh0en, rhoh0_edge_new);
+
+    m.MakeRhoHFlux(st, sf, se, um, w0mac, b_r0o, b_r0eo, r0o, b_r0n, b_r0en, r0n, b_rh0o,
+                   b_rh0eo, rh0o, b_rh0n, b_rh0en, rh0n, h0o, h0n);
+    return 0;
+}
+
+// Maestro::CelltoEdge, Source/MaestroCelltoEdge.cpp:5 — one level, one chunk [r_lo, r_hi]
+int ref_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi) {
+    Maestro m;
+    maestro::spherical = false;
+    // base_geom tables: BaseStateArray views over local storage
+    int nr_tab[1] = {nr};
+    int chunks[1] = {1};
+    int rs[2] = {0, r_lo};
+    int re[2] = {0, r_hi};
+    m.base_geom.finest_radial_level = 0;
+    m.base_geom.nr.init(nr_tab, 1, 1, 1);
+    m.base_geom.numdisjointchunks.init(chunks, 1, 1, 1);
+    m.base_geom.r_start_coord.init(rs, 1, 2, 1);
+    m.base_geom.r_end_coord.init(re, 1, 2, 1);
+
+    BaseState<Real> c(1, nr, 1), e(1, nr + 1, 1);
+    auto ca = c.array();
+    auto ea = e.array();
+    for (int i = 0; i < nr; ++i) ca(i) = cell[i];
+    for (int i = 0; i <= nr; ++i) ea(i) = edge[i];
+    m.CelltoEdge(c, e);
+    for (int i = 0; i <= nr; ++i) edge[i] = ea(i);
+    return 0;
+}
+
+}  // extern "C"
