@@ -1,0 +1,697 @@
+// mx_api.cu — the C ABI of libmxadv.so (include/mxadv.h): argument validation, pointer
+// residency (device / managed / host), stream-ordered device workspace, host staging, and
+// dispatch to the fused (mx_fused.cu) or staged (mx_staged.cu) kernels.  No CPU compute
+// path exists: without a CUDA device every compute entry point returns MX_ERR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "mx_common.h"
+#include "mx_flux.h"
+#include "mx_fused.h"
+#include "mx_staged.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_OK(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(MX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));     \
+    } while (0)
+
+int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MX_ERR_NO_DEVICE,
+                    "no CUDA device available; libmxadv has no CPU fallback (%s)",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    static bool pool_init = false;
+    if (!pool_init) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;  // keep freed workspace cached in the pool
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_init = true;
+    }
+    return MX_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    if (p == nullptr) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// One API call's worth of device mirrors for host-resident arguments.
+class Session {
+   public:
+    explicit Session(void* stream) : st_(static_cast<cudaStream_t>(stream)) {}
+    ~Session() {
+        for (void* p : owned_) cudaFreeAsync(p, st_);
+    }
+    cudaStream_t stream() const { return st_; }
+    bool any_host() const { return any_host_; }
+
+    cudaError_t alloc(void** p, size_t bytes) {
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 8, st_);
+        if (e == cudaSuccess) owned_.push_back(*p);
+        return e;
+    }
+
+    // Device view of a fab.  Host fabs get a full-size device mirror; components
+    // [c0, c0+nc) are uploaded when `in`, and registered for download when `out`.
+    int fab(const MxFab* f, DFab* out, int c0, int nc, bool in, bool outp) {
+        if (f == nullptr || f->p == nullptr) return fail(MX_ERR_INVALID, "null fab");
+        if (c0 < 0 || nc < 0 || c0 + nc > f->ncomp)
+            return fail(MX_ERR_INVALID, "component range [%d,%d) outside fab with %d comps", c0,
+                        c0 + nc, f->ncomp);
+        for (int d = 0; d < 3; ++d)
+            if (f->hi[d] < f->lo[d]) return fail(MX_ERR_INVALID, "empty fab box");
+        if (is_device_ptr(f->p)) {
+            *out = make_dfab(f, f->p);
+            return MX_OK;
+        }
+        any_host_ = true;
+        DFab d = make_dfab(f, nullptr);
+        void* dev = nullptr;
+        CUDA_OK(alloc(&dev, sizeof(double) * (size_t)d.sn * f->ncomp));
+        d.p = static_cast<double*>(dev);
+        if (in && nc > 0) {
+            CUDA_OK(cudaMemcpyAsync(d.p + (size_t)c0 * d.sn, f->p + (size_t)c0 * d.sn,
+                                    sizeof(double) * (size_t)d.sn * nc, cudaMemcpyHostToDevice,
+                                    st_));
+            h2d_ += sizeof(double) * (size_t)d.sn * nc;
+        }
+        if (outp && nc > 0) {
+            backs_.push_back({f->p + (size_t)c0 * d.sn, d.p + (size_t)c0 * d.sn,
+                              sizeof(double) * (size_t)d.sn * nc});
+        }
+        *out = d;
+        return MX_OK;
+    }
+
+    // extra upload of another component range into an existing host mirror
+    int upload(const MxFab* f, const DFab& d, int c0, int nc) {
+        if (is_device_ptr(f->p) || nc <= 0) return MX_OK;
+        CUDA_OK(cudaMemcpyAsync(d.p + (size_t)c0 * d.sn, f->p + (size_t)c0 * d.sn,
+                                sizeof(double) * (size_t)d.sn * nc, cudaMemcpyHostToDevice,
+                                st_));
+        return MX_OK;
+    }
+    int download_later(const MxFab* f, const DFab& d, int c0, int nc) {
+        if (is_device_ptr(f->p) || nc <= 0) return MX_OK;
+        backs_.push_back({f->p + (size_t)c0 * d.sn, d.p + (size_t)c0 * d.sn,
+                          sizeof(double) * (size_t)d.sn * nc});
+        return MX_OK;
+    }
+
+    // 1-D base-state array at level `lev` -> device pointer + stride
+    int base(const MxBase* b, int lev, const double** p, int* stride) {
+        *p = nullptr;
+        *stride = 1;
+        if (b == nullptr || b->p == nullptr) return MX_OK;
+        if (lev < 0 || lev >= b->nlev) return fail(MX_ERR_INVALID, "base-state level %d", lev);
+        const size_t n = (size_t)b->nlev * b->len * b->nvar;
+        const double* base = b->p;
+        if (!is_device_ptr(b->p)) {
+            void* dev = nullptr;
+            CUDA_OK(alloc(&dev, sizeof(double) * n));
+            CUDA_OK(cudaMemcpyAsync(dev, b->p, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
+            base = static_cast<const double*>(dev);
+        }
+        *p = base + (size_t)lev * b->len * b->nvar;
+        *stride = b->nvar;
+        return MX_OK;
+    }
+
+    // copy results back to host fabs and wait (host callers get synchronous semantics)
+    int finish() {
+        CUDA_OK(cudaGetLastError());
+        for (auto& b : backs_) {
+            CUDA_OK(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st_));
+        }
+        if (any_host_) CUDA_OK(cudaStreamSynchronize(st_));
+        return MX_OK;
+    }
+
+   private:
+    struct Back {
+        double* host;
+        const double* dev;
+        size_t bytes;
+    };
+    cudaStream_t st_;
+    std::vector<void*> owned_;
+    std::vector<Back> backs_;
+    bool any_host_ = false;
+    size_t h2d_ = 0;
+};
+
+#define MX_TRY(expr)              \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != MX_OK) return rc__; \
+    } while (0)
+
+int check_geom(const MxGeom* g) {
+    if (g == nullptr) return fail(MX_ERR_INVALID, "null geometry");
+    if (g->dim != 2 && g->dim != 3) return fail(MX_ERR_INVALID, "dim must be 2 or 3");
+    for (int d = 0; d < g->dim; ++d) {
+        if (g->valid_hi[d] < g->valid_lo[d]) return fail(MX_ERR_INVALID, "empty valid box");
+        if (!(g->dx[d] > 0.0)) return fail(MX_ERR_INVALID, "dx must be positive");
+    }
+    return MX_OK;
+}
+
+// fab must cover grow(valid, ng) (+1 face in `nodal_dir`)
+int check_cover(const MxGeom* g, const MxFab* f, int ng, int nodal_dir, const char* name) {
+    for (int d = 0; d < g->dim; ++d) {
+        const int hi = g->valid_hi[d] + (d == nodal_dir ? 1 : 0);
+        if (f->lo[d] > g->valid_lo[d] - ng || f->hi[d] < hi + ng)
+            return fail(MX_ERR_INVALID, "%s needs %d ghost cell(s) in direction %d", name, ng, d);
+    }
+    return MX_OK;
+}
+
+// true when the fab box is exactly the valid box made nodal in `nodal_dir` (no ghosts): every
+// entry of the swept components is then overwritten and a host mirror needs no upload
+bool exact_face_box(const MxGeom* g, const MxFab* f, int nodal_dir) {
+    for (int d = 0; d < g->dim; ++d) {
+        const int hi = g->valid_hi[d] + (d == nodal_dir ? 1 : 0);
+        if (f->lo[d] != g->valid_lo[d] || f->hi[d] != hi) return false;
+    }
+    return true;
+}
+
+int check_edge_params(const MxGeom* g, const MxEdgeParams* p) {
+    if (p == nullptr || p->bc == nullptr) return fail(MX_ERR_INVALID, "null edge parameters");
+    if (p->ppm_type < 0 || p->ppm_type > 2)
+        return fail(MX_ERR_UNSUPPORTED, "ppm_type %d (reference supports 0, 1, 2)", p->ppm_type);
+    if (p->ppm_type == 0 && p->slope_order != 0 && p->slope_order != 2 && p->slope_order != 4)
+        return fail(MX_ERR_UNSUPPORTED, "slope_order %d (reference supports 0, 2, 4)",
+                    p->slope_order);
+    if (p->num_comp < 0 || p->start_scomp < 0) return fail(MX_ERR_INVALID, "bad component range");
+    if (p->start_bccomp < 0 || p->start_bccomp + p->num_comp > p->nbccomp)
+        return fail(MX_ERR_INVALID, "bc table too short");
+    (void)g;
+    return MX_OK;
+}
+
+KEdge make_kedge(const MxEdgeParams* p) {
+    KEdge e;
+    memset(&e, 0, sizeof(e));
+    e.dt = p->dt;
+    e.eps = p->rel_eps;
+    e.ppm_type = p->ppm_type;
+    e.slope_order = p->slope_order;
+    e.trace = p->ppm_trace_forces;
+    e.is_vel = p->is_vel;
+    e.is_cons = p->is_conservative;
+    return e;
+}
+
+struct EdgeArgs {
+    DFab state, force, sedge[3], umac[3];
+};
+
+int stage_edge_args(Session& S, const MxGeom* g, const MxFab* state, const MxFab* sedge,
+                    const MxFab* umac, const MxFab* force, const MxEdgeParams* p, EdgeArgs* a) {
+    const int ng_s = p->ppm_type == 2 ? 4 : 3;
+    MX_TRY(check_cover(g, state, ng_s, -1, "state"));
+    MX_TRY(check_cover(g, force, (p->ppm_trace_forces && p->ppm_type != 0) ? ng_s : 1, -1,
+                       "force"));
+    MX_TRY(S.fab(state, &a->state, p->start_scomp, p->num_comp, true, false));
+    MX_TRY(S.fab(force, &a->force, p->start_scomp, p->num_comp, true, false));
+    for (int d = 0; d < g->dim; ++d) {
+        MX_TRY(check_cover(g, &umac[d], 1, d, "umac"));
+        MX_TRY(check_cover(g, &sedge[d], 0, d, "sedge"));
+        if (umac[d].ncomp < 1) return fail(MX_ERR_INVALID, "umac has no components");
+        MX_TRY(S.fab(&umac[d], &a->umac[d], 0, 1, true, false));
+        MX_TRY(S.fab(&sedge[d], &a->sedge[d], p->start_scomp, p->num_comp,
+                     !exact_face_box(g, &sedge[d], d), true));
+    }
+    if (g->dim == 2) {
+        a->umac[2] = a->umac[0];
+        a->sedge[2] = a->sedge[0];
+    }
+    return MX_OK;
+}
+
+int run_edge(Session& S, const KGeom& kg, const MxEdgeParams* p, const EdgeArgs& a) {
+    KEdge e = make_kedge(p);
+    if (p->num_comp == 0) return MX_OK;
+    if (fused_edge_supported(kg, e)) {
+        return fused_edge_scal(kg, e, p, a.state, a.sedge, a.umac, a.force, S.stream()) == 0
+                   ? MX_OK
+                   : fail(MX_ERR_CUDA, "fused edge kernel launch failed");
+    }
+    void* scratch = nullptr;
+    CUDA_OK(S.alloc(&scratch, sizeof(double) * staged_scratch_doubles(kg)));
+    staged_make_edge_scal(kg, e, p, a.state, a.sedge, a.umac, a.force,
+                          static_cast<double*>(scratch), S.stream());
+    return MX_OK;
+}
+
+int fill_kflux(Session& S, const MxFluxParams* p, const MxBase* rho0_old,
+               const MxBase* rho0_edge_old, const MxBase* rho0_new, const MxBase* rho0_edge_new,
+               const MxBase* rho0_pred, const MxBase* w0, const MxBase* rhoh0_old,
+               const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+               const MxBase* rhoh0_edge_new, KFlux* f) {
+    memset(f, 0, sizeof(*f));
+    f->spt = p->species_pred_type;
+    f->ept = p->enthalpy_pred_type;
+    f->spherical = p->spherical;
+    f->exact = p->use_exact_base_state;
+    f->evolve = p->evolve_base_state;
+    f->rho = p->rho_comp;
+    f->rhoh = p->rhoh_comp;
+    f->first_spec = p->first_spec;
+    f->num_spec = p->num_spec;
+    f->start_comp = p->start_comp;
+    f->num_comp = p->num_comp;
+    MX_TRY(S.base(rho0_old, p->lev, &f->rho0_old, &f->st_rho0_old));
+    MX_TRY(S.base(rho0_new, p->lev, &f->rho0_new, &f->st_rho0_new));
+    MX_TRY(S.base(rho0_edge_old, p->lev, &f->rho0_edge_old, &f->st_rho0_edge_old));
+    MX_TRY(S.base(rho0_edge_new, p->lev, &f->rho0_edge_new, &f->st_rho0_edge_new));
+    MX_TRY(S.base(rho0_pred, p->lev, &f->rho0_pred_edge, &f->st_rho0_pred_edge));
+    MX_TRY(S.base(w0, p->lev, &f->w0, &f->st_w0));
+    MX_TRY(S.base(rhoh0_old, p->lev, &f->rhoh0_old, &f->st_rhoh0_old));
+    MX_TRY(S.base(rhoh0_new, p->lev, &f->rhoh0_new, &f->st_rhoh0_new));
+    MX_TRY(S.base(rhoh0_edge_old, p->lev, &f->rhoh0_edge_old, &f->st_rhoh0_edge_old));
+    MX_TRY(S.base(rhoh0_edge_new, p->lev, &f->rhoh0_edge_new, &f->st_rhoh0_edge_new));
+    return MX_OK;
+}
+
+int stage_mac(Session& S, const MxGeom* g, const MxFab* src, DFab* dst, const char* name) {
+    if (src == nullptr) return fail(MX_ERR_INVALID, "%s is required when spherical", name);
+    for (int d = 0; d < 3; ++d) {
+        MX_TRY(check_cover(g, &src[d], 0, d, name));
+        MX_TRY(S.fab(&src[d], &dst[d], 0, 1, true, false));
+    }
+    return MX_OK;
+}
+
+int need_base(const MxBase* b, const char* name) {
+    if (b == nullptr || b->p == nullptr) return fail(MX_ERR_INVALID, "%s is required", name);
+    return MX_OK;
+}
+
+}  // namespace
+
+void mx_count_launch(int n) { g_launches += n; }
+
+extern "C" {
+
+int mx_abi_version(void) { return MXADV_ABI_VERSION; }
+const char* mx_last_error(void) { return g_err.c_str(); }
+
+int mx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+long long mx_launch_count(void) { return g_launches.load(); }
+void mx_reset_launch_count(void) { g_launches = 0; }
+
+int mx_free_workspace(void) {
+    MX_TRY(require_device());
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemPoolTrimTo(pool, 0));
+    return MX_OK;
+}
+
+int mx_make_edge_scal(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                      const MxFab* umac, const MxFab* force, const MxEdgeParams* par,
+                      void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!state || !sedge || !umac || !force) return fail(MX_ERR_INVALID, "null fab argument");
+    MX_TRY(check_edge_params(geom, par));
+    MX_TRY(require_device());
+    Session S(stream);
+    EdgeArgs a;
+    MX_TRY(stage_edge_args(S, geom, state, sedge, umac, force, par, &a));
+    const KGeom kg = make_kgeom(geom);
+    MX_TRY(run_edge(S, kg, par, a));
+    return S.finish();
+}
+
+int mx_make_rhoX_flux(const MxGeom* geom, const MxFab* sflux, const MxFab* etarhoflux,
+                      const MxFab* sedge, const MxFab* umac, const MxBase* rho0_old,
+                      const MxBase* rho0_edge_old, const MxFab* r0mac_old,
+                      const MxBase* rho0_new, const MxBase* rho0_edge_new,
+                      const MxFab* r0mac_new, const MxBase* rho0_predicted_edge,
+                      const MxBase* w0, const MxFluxParams* par, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!sflux || !sedge || !umac || !par) return fail(MX_ERR_INVALID, "null argument");
+    if (par->species_pred_type < 1 || par->species_pred_type > 3)
+        return fail(MX_ERR_UNSUPPORTED, "species_pred_type %d", par->species_pred_type);
+    MX_TRY(require_device());
+    const bool sph = geom->dim == 3 && par->spherical;
+    const bool do_eta = !sph && par->evolve_base_state && !par->use_exact_base_state;
+    if (!sph && par->species_pred_type == MX_PRED_RHOPRIME_AND_X) {
+        MX_TRY(need_base(rho0_old, "rho0_old"));
+        MX_TRY(need_base(rho0_new, "rho0_new"));
+        MX_TRY(need_base(rho0_edge_old, "rho0_edge_old"));
+        MX_TRY(need_base(rho0_edge_new, "rho0_edge_new"));
+    }
+    if (do_eta) {
+        if (!etarhoflux) return fail(MX_ERR_INVALID, "etarhoflux is required");
+        MX_TRY(need_base(w0, "w0"));
+        MX_TRY(need_base(rho0_predicted_edge, "rho0_predicted_edge"));
+    }
+    Session S(stream);
+    KFlux f;
+    MX_TRY(fill_kflux(S, par, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new,
+                      rho0_predicted_edge, w0, nullptr, nullptr, nullptr, nullptr, &f));
+    const KGeom kg = make_kgeom(geom);
+    DFab sf[3], se[3], um[3], eta;
+    KMac mac;
+    memset(&mac, 0, sizeof(mac));
+    memset(&eta, 0, sizeof(eta));
+    for (int d = 0; d < geom->dim; ++d) {
+        MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
+        MX_TRY(check_cover(geom, &sedge[d], 0, d, "sedge"));
+        MX_TRY(check_cover(geom, &umac[d], 0, d, "umac"));
+        // species components in/out; the Rho component of sedge is an input, of sflux an output
+        const bool keep = !exact_face_box(geom, &sflux[d], d);
+        MX_TRY(S.fab(&sflux[d], &sf[d], par->start_comp, par->num_comp, keep, true));
+        if (keep) MX_TRY(S.upload(&sflux[d], sf[d], par->rho_comp, 1));
+        MX_TRY(S.download_later(&sflux[d], sf[d], par->rho_comp, 1));
+        MX_TRY(S.fab(&sedge[d], &se[d], par->start_comp, par->num_comp, true, false));
+        MX_TRY(S.upload(&sedge[d], se[d], par->rho_comp, 1));
+        MX_TRY(S.fab(&umac[d], &um[d], 0, 1, true, false));
+    }
+    if (do_eta) {
+        MX_TRY(check_cover(geom, etarhoflux, 0, geom->dim - 1, "etarhoflux"));
+        MX_TRY(S.fab(etarhoflux, &eta, 0, 1, true, true));
+    }
+    if (sph) {
+        MX_TRY(stage_mac(S, geom, r0mac_old, mac.r0_old, "r0mac_old"));
+        MX_TRY(stage_mac(S, geom, r0mac_new, mac.r0_new, "r0mac_new"));
+    }
+    flux_rhoX(kg, f, sf, eta, se, um, mac, S.stream());
+    return S.finish();
+}
+
+int mx_make_rhoh_flux(const MxGeom* geom, const MxFab* sflux, const MxFab* sedge,
+                      const MxFab* umac, const MxBase* rho0_old, const MxBase* rho0_edge_old,
+                      const MxFab* r0mac_old, const MxBase* rho0_new,
+                      const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                      const MxBase* rhoh0_old, const MxBase* rhoh0_edge_old,
+                      const MxFab* rh0mac_old, const MxBase* rhoh0_new,
+                      const MxBase* rhoh0_edge_new, const MxFab* rh0mac_new,
+                      const MxFab* h0mac_old, const MxFab* h0mac_new, const MxFluxParams* par,
+                      void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!sflux || !sedge || !umac || !par) return fail(MX_ERR_INVALID, "null argument");
+    if (par->enthalpy_pred_type < 0 || par->enthalpy_pred_type > 6)
+        return fail(MX_ERR_UNSUPPORTED, "enthalpy_pred_type %d", par->enthalpy_pred_type);
+    MX_TRY(require_device());
+    const bool sph = geom->dim == 3 && par->spherical;
+    const int ept = par->enthalpy_pred_type;
+    const bool have_h =
+        ept == MX_PRED_H || ept == MX_PRED_T_THEN_H || ept == MX_PRED_TPRIME_THEN_H;
+    if (!sph) {
+        if (have_h && par->species_pred_type == MX_PRED_RHOPRIME_AND_X) {
+            MX_TRY(need_base(rho0_old, "rho0_old"));
+            MX_TRY(need_base(rho0_new, "rho0_new"));
+            MX_TRY(need_base(rho0_edge_old, "rho0_edge_old"));
+            MX_TRY(need_base(rho0_edge_new, "rho0_edge_new"));
+        }
+        if (ept == MX_PRED_RHOHPRIME || ept == MX_PRED_T_THEN_RHOHPRIME) {
+            MX_TRY(need_base(rhoh0_old, "rhoh0_old"));
+            MX_TRY(need_base(rhoh0_new, "rhoh0_new"));
+            MX_TRY(need_base(rhoh0_edge_old, "rhoh0_edge_old"));
+            MX_TRY(need_base(rhoh0_edge_new, "rhoh0_edge_new"));
+        }
+    }
+    Session S(stream);
+    KFlux f;
+    MX_TRY(fill_kflux(S, par, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, nullptr, nullptr,
+                      rhoh0_old, rhoh0_edge_old, rhoh0_new, rhoh0_edge_new, &f));
+    const KGeom kg = make_kgeom(geom);
+    DFab sf[3], se[3], um[3];
+    KMac mac;
+    memset(&mac, 0, sizeof(mac));
+    for (int d = 0; d < geom->dim; ++d) {
+        MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
+        MX_TRY(check_cover(geom, &sedge[d], 0, d, "sedge"));
+        MX_TRY(check_cover(geom, &umac[d], 0, d, "umac"));
+        // the reference leaves sflux(RhoH) untouched for some option combinations: in + out
+        MX_TRY(S.fab(&sflux[d], &sf[d], par->rhoh_comp, 1, true, true));
+        MX_TRY(S.fab(&sedge[d], &se[d], par->rhoh_comp, 1, true, false));
+        MX_TRY(S.upload(&sedge[d], se[d], par->rho_comp, 1));
+        MX_TRY(S.fab(&umac[d], &um[d], 0, 1, true, false));
+    }
+    if (sph) {
+        if (par->use_exact_base_state) {
+            MX_TRY(stage_mac(S, geom, rh0mac_old, mac.rh0_old, "rh0mac_old"));
+            MX_TRY(stage_mac(S, geom, rh0mac_new, mac.rh0_new, "rh0mac_new"));
+        } else {
+            MX_TRY(stage_mac(S, geom, r0mac_old, mac.r0_old, "r0mac_old"));
+            MX_TRY(stage_mac(S, geom, r0mac_new, mac.r0_new, "r0mac_new"));
+            MX_TRY(stage_mac(S, geom, h0mac_old, mac.h0_old, "h0mac_old"));
+            MX_TRY(stage_mac(S, geom, h0mac_new, mac.h0_new, "h0mac_new"));
+        }
+    }
+    flux_rhoh(kg, f, sf, se, um, mac, S.stream());
+    return S.finish();
+}
+
+int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                         const MxFab* sflux, const MxFab* etarhoflux, const MxFab* umac,
+                         const MxFab* force, const MxEdgeParams* epar, int rho_bccomp,
+                         const MxBase* rho0_old, const MxBase* rho0_edge_old,
+                         const MxFab* r0mac_old, const MxBase* rho0_new,
+                         const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                         const MxBase* rho0_predicted_edge, const MxBase* w0,
+                         const MxFluxParams* fpar, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!state || !sedge || !sflux || !umac || !force || !fpar)
+        return fail(MX_ERR_INVALID, "null argument");
+    MX_TRY(check_edge_params(geom, epar));
+    if (geom->dim != 3) return fail(MX_ERR_UNSUPPORTED, "mx_density_edge_flux is 3-D only");
+    if (epar->is_vel || epar->is_conservative)
+        return fail(MX_ERR_UNSUPPORTED,
+                    "mx_density_edge_flux: is_vel / is_conservative sweeps use mx_make_edge_scal");
+    if (fpar->species_pred_type != MX_PRED_RHOPRIME_AND_X &&
+        fpar->species_pred_type != MX_PRED_RHO_AND_X)
+        return fail(MX_ERR_UNSUPPORTED,
+                    "mx_density_edge_flux: species_pred_type %d predicts (rho X) conservatively; "
+                    "use mx_make_edge_scal + mx_make_rhoX_flux",
+                    fpar->species_pred_type);
+    if (epar->start_scomp != fpar->start_comp || epar->num_comp != fpar->num_comp)
+        return fail(MX_ERR_INVALID, "edge and flux component ranges differ");
+    if (rho_bccomp < 0 || rho_bccomp >= epar->nbccomp)
+        return fail(MX_ERR_INVALID, "rho_bccomp outside bc table");
+    MX_TRY(require_device());
+    const bool sph = fpar->spherical != 0;
+    const bool do_eta = !sph && fpar->evolve_base_state && !fpar->use_exact_base_state;
+    if (do_eta && !etarhoflux) return fail(MX_ERR_INVALID, "etarhoflux is required");
+
+    Session S(stream);
+    KFlux f;
+    MX_TRY(fill_kflux(S, fpar, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new,
+                      rho0_predicted_edge, w0, nullptr, nullptr, nullptr, nullptr, &f));
+    const KGeom kg = make_kgeom(geom);
+    const int ng_s = epar->ppm_type == 2 ? 4 : 3;
+    MX_TRY(check_cover(geom, state, ng_s, -1, "state"));
+    MX_TRY(check_cover(geom, force, 1, -1, "force"));
+    const int rho = fpar->rho_comp;
+    EdgeArgs a;
+    MX_TRY(S.fab(state, &a.state, epar->start_scomp, epar->num_comp, true, false));
+    MX_TRY(S.upload(state, a.state, rho, 1));
+    MX_TRY(S.fab(force, &a.force, epar->start_scomp, epar->num_comp, true, false));
+    MX_TRY(S.upload(force, a.force, rho, 1));
+    DFab sf[3], eta;
+    memset(&eta, 0, sizeof(eta));
+    KMac mac;
+    memset(&mac, 0, sizeof(mac));
+    for (int d = 0; d < 3; ++d) {
+        MX_TRY(check_cover(geom, &umac[d], 1, d, "umac"));
+        MX_TRY(check_cover(geom, &sedge[d], 0, d, "sedge"));
+        MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
+        MX_TRY(S.fab(&umac[d], &a.umac[d], 0, 1, true, false));
+        const bool keep_e = !exact_face_box(geom, &sedge[d], d);
+        const bool keep_f = !exact_face_box(geom, &sflux[d], d);
+        MX_TRY(S.fab(&sedge[d], &a.sedge[d], epar->start_scomp, epar->num_comp, keep_e, true));
+        if (keep_e) MX_TRY(S.upload(&sedge[d], a.sedge[d], rho, 1));
+        MX_TRY(S.download_later(&sedge[d], a.sedge[d], rho, 1));
+        MX_TRY(S.fab(&sflux[d], &sf[d], epar->start_scomp, epar->num_comp, keep_f, true));
+        if (keep_f) MX_TRY(S.upload(&sflux[d], sf[d], rho, 1));
+        MX_TRY(S.download_later(&sflux[d], sf[d], rho, 1));
+    }
+    if (do_eta) {
+        MX_TRY(check_cover(geom, etarhoflux, 0, 2, "etarhoflux"));
+        MX_TRY(S.fab(etarhoflux, &eta, 0, 1, true, true));
+    }
+    if (sph) {
+        MX_TRY(stage_mac(S, geom, r0mac_old, mac.r0_old, "r0mac_old"));
+        MX_TRY(stage_mac(S, geom, r0mac_new, mac.r0_new, "r0mac_new"));
+    }
+    KEdge e = make_kedge(epar);
+    if (fused_density_supported(kg, e, f)) {
+        if (fused_density(kg, e, epar, rho_bccomp, f, a.state, a.sedge, sf, eta, a.umac, a.force,
+                          mac, S.stream()) != 0)
+            return fail(MX_ERR_CUDA, "fused density kernel launch failed");
+        return S.finish();
+    }
+    // composition of the three reference calls (MaestroDensityAdvance.cpp:115,128,182)
+    MX_TRY(run_edge(S, kg, epar, a));
+    MxEdgeParams rpar = *epar;
+    rpar.start_scomp = rho;
+    rpar.start_bccomp = rho_bccomp;
+    rpar.num_comp = 1;
+    MX_TRY(run_edge(S, kg, &rpar, a));
+    flux_rhoX(kg, f, sf, eta, a.sedge, a.umac, mac, S.stream());
+    return S.finish();
+}
+
+int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                          const MxFab* sflux, const MxFab* umac, const MxFab* force,
+                          const MxEdgeParams* epar, const MxBase* rho0_old,
+                          const MxBase* rho0_edge_old, const MxBase* rho0_new,
+                          const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
+                          const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+                          const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
+                          void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!state || !sedge || !sflux || !umac || !force || !fpar)
+        return fail(MX_ERR_INVALID, "null argument");
+    MX_TRY(check_edge_params(geom, epar));
+    if (geom->dim != 3 || fpar->spherical)
+        return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_edge_flux is 3-D planar only");
+    if (epar->is_vel) return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_edge_flux: is_vel");
+    if (epar->num_comp != 1 || epar->start_scomp != fpar->rhoh_comp)
+        return fail(MX_ERR_INVALID, "mx_enthalpy_edge_flux sweeps the single component RhoH");
+    const int ept = fpar->enthalpy_pred_type;
+    if (ept == MX_PRED_T_THEN_RHOHPRIME || ept == MX_PRED_T_THEN_H ||
+        ept == MX_PRED_TPRIME_THEN_H)
+        return fail(MX_ERR_UNSUPPORTED,
+                    "enthalpy_pred_type %d needs the EOS between edge prediction and flux "
+                    "(HfromRhoTedge); call mx_make_edge_scal and mx_make_rhoh_flux separately",
+                    ept);
+    MX_TRY(require_device());
+    Session S(stream);
+    KFlux f;
+    MX_TRY(fill_kflux(S, fpar, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, nullptr, nullptr,
+                      rhoh0_old, rhoh0_edge_old, rhoh0_new, rhoh0_edge_new, &f));
+    const KGeom kg = make_kgeom(geom);
+    EdgeArgs a;
+    MX_TRY(stage_edge_args(S, geom, state, sedge, umac, force, epar, &a));
+    DFab sf[3];
+    KMac mac;
+    memset(&mac, 0, sizeof(mac));
+    for (int d = 0; d < 3; ++d) {
+        MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
+        MX_TRY(S.fab(&sflux[d], &sf[d], fpar->rhoh_comp, 1, true, true));
+        MX_TRY(S.upload(&sedge[d], a.sedge[d], fpar->rho_comp, 1));
+    }
+    MX_TRY(run_edge(S, kg, epar, a));
+    flux_rhoh(kg, f, sf, a.sedge, a.umac, mac, S.stream());
+    return S.finish();
+}
+
+int mx_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi, void* stream) {
+    if (!cell || !edge || nr < 1 || r_lo < 0 || r_hi >= nr || r_hi < r_lo)
+        return fail(MX_ERR_INVALID, "bad cell_to_edge arguments");
+    MX_TRY(require_device());
+    Session S(stream);
+    const double* dc = cell;
+    double* de = edge;
+    const bool hc = !is_device_ptr(cell), he = !is_device_ptr(edge);
+    if (hc) {
+        void* p;
+        CUDA_OK(S.alloc(&p, sizeof(double) * nr));
+        CUDA_OK(cudaMemcpyAsync(p, cell, sizeof(double) * nr, cudaMemcpyHostToDevice, S.stream()));
+        dc = static_cast<const double*>(p);
+    }
+    if (he) {
+        void* p;
+        CUDA_OK(S.alloc(&p, sizeof(double) * (nr + 1)));
+        CUDA_OK(cudaMemcpyAsync(p, edge, sizeof(double) * (nr + 1), cudaMemcpyHostToDevice,
+                                S.stream()));
+        de = static_cast<double*>(p);
+    }
+    cell_to_edge(dc, de, nr, r_lo, r_hi, S.stream());
+    CUDA_OK(cudaGetLastError());
+    if (he) {
+        CUDA_OK(cudaMemcpyAsync(edge, de, sizeof(double) * (nr + 1), cudaMemcpyDeviceToHost,
+                                S.stream()));
+    }
+    if (hc || he) CUDA_OK(cudaStreamSynchronize(S.stream()));
+    return MX_OK;
+}
+
+long long mx_halo_count(const MxGeom* geom, const MxFab* fab, int dir, int ng, int ncomp) {
+    if (!geom || !fab || dir < 0 || dir >= geom->dim) return 0;
+    long long n = ncomp;
+    for (int d = 0; d < 3; ++d) n *= (d == dir) ? ng : (fab->hi[d] - fab->lo[d] + 1);
+    return n;
+}
+
+static int halo_common(const MxGeom* geom, const MxFab* fab, int dir, int side, int ng,
+                       int comp0, int ncomp, double* buf, bool unpack, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!fab || !buf) return fail(MX_ERR_INVALID, "null argument");
+    if (dir < 0 || dir >= geom->dim || (side != 0 && side != 1) || ng < 1)
+        return fail(MX_ERR_INVALID, "bad halo slab");
+    if (comp0 < 0 || comp0 + ncomp > fab->ncomp) return fail(MX_ERR_INVALID, "bad components");
+    const int nghost = geom->valid_lo[dir] - fab->lo[dir];
+    if (ng > nghost) return fail(MX_ERR_INVALID, "fab has only %d ghost cells", nghost);
+    MX_TRY(require_device());
+    if (!is_device_ptr(fab->p) || !is_device_ptr(buf))
+        return fail(MX_ERR_UNSUPPORTED, "halo pack/unpack operates on device memory only");
+    const KGeom kg = make_kgeom(geom);
+    DFab d = make_dfab(fab, fab->p);
+    halo_pack(kg, d, dir, side, ng, comp0, ncomp, buf, unpack, static_cast<cudaStream_t>(stream));
+    CUDA_OK(cudaGetLastError());
+    return MX_OK;
+}
+
+int mx_halo_pack(const MxGeom* geom, const MxFab* fab, int dir, int side, int ng, int comp0,
+                 int ncomp, double* buf, void* stream) {
+    return halo_common(geom, fab, dir, side, ng, comp0, ncomp, buf, false, stream);
+}
+int mx_halo_unpack(const MxGeom* geom, const MxFab* fab, int dir, int side, int ng, int comp0,
+                   int ncomp, const double* buf, void* stream) {
+    return halo_common(geom, fab, dir, side, ng, comp0, ncomp, const_cast<double*>(buf), true,
+                       stream);
+}
+
+}  // extern "C"

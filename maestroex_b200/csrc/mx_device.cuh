@@ -1,0 +1,452 @@
+// mx_device.cuh — fp64 device arithmetic of the Godunov edge-state predictor, written once
+// and direction-generic, shared by the staged (mx_staged.cu) and fused (mx_fused.cu) kernels.
+//
+// Parity contract: every function reproduces the reference expression tree (association
+// included) so that with FMA contraction off (-fmad=false; the reference CPU build has no
+// FMA either) results are bit-identical to
+//   Source/MaestroSlopes.cpp, Source/MaestroPPM.cpp, Source/MaestroMakeEdgeScalars.cpp.
+// Deliberate, result-preserving departures from the literal source:
+//   * x / 6.0 and x / 3.0 use a 3-instruction correctly-rounded sequence (div_c) instead of
+//     the ~25-instruction IEEE division routine; explicit __fma_rn, independent of -fmad;
+//   * copysign(1.0, a) * m with m >= 0 is formed as copysign(m, a) on the integer pipe;
+//   * |x| uses the free operand modifier; min/max follow std::min/std::max (amrex::min/max),
+//     not fmin/fmax, so ties and signed zeros select the same operand as the reference.
+#ifndef MX_DEVICE_CUH
+#define MX_DEVICE_CUH
+
+#include <cuda_runtime.h>
+
+#define MXD __device__ __forceinline__
+
+namespace mxd {
+
+constexpr int BC_REFLECT_ODD = -1;
+constexpr int BC_REFLECT_EVEN = 1;
+constexpr int BC_FOEXTRAP = 2;
+constexpr int BC_EXT_DIR = 3;
+constexpr int BC_HOEXTRAP = 4;
+
+MXD double dmin_(double a, double b) { return (b < a) ? b : a; }
+MXD double dmax_(double a, double b) { return (a < b) ? b : a; }
+
+// copysign(1.0, sgn) * mag for mag >= +0 (exact: +-1 * mag only flips the sign bit)
+MXD double signed_mag(double mag, double sgn) {
+    return __hiloint2double((__double2hiint(mag) & 0x7fffffff) | (__double2hiint(sgn) & 0x80000000),
+                            __double2loint(mag));
+}
+MXD double sign1(double sgn) { return signed_mag(1.0, sgn); }
+
+// Correctly rounded x / c for the compile-time constants c = 6 and c = 3 (Markstein-style:
+// q0 = RN(x * RN(1/c)), r = x - c*q0 exactly via FMA, q = RN(q0 + r * RN(1/c))).  Verified
+// against IEEE division on 5.5e8 random and structured operands per divisor
+// (tests/test_divconst.py restates the check on the host); no over/underflow in range.
+MXD double div6(double x) {
+    const double y = 1.0 / 6.0;
+    const double q = __dmul_rn(x, y);
+    const double r = __fma_rn(-6.0, q, x);
+    return __fma_rn(r, y, q);
+}
+MXD double div3(double x) {
+    const double y = 1.0 / 3.0;
+    const double q = __dmul_rn(x, y);
+    const double r = __fma_rn(-3.0, q, x);
+    return __fma_rn(r, y, q);
+}
+
+// ---------------------------------------------------------------------------------------
+// Slopes (ppm_type == 0): Source/MaestroSlopes.cpp:6-601.  S[o+2] = s at offset o in [-2,2]
+// along the sweep direction; I = cell index along that direction; lo/hi = domain bounds;
+// lobc/hibc = (bc == ext_dir || bc == hoextrap); xquirk = sweep direction is x.
+// ---------------------------------------------------------------------------------------
+MXD double mc_lim(double dpls, double dmn) {
+    const double slim = dmin_(fabs(dpls), fabs(dmn));
+    return dpls * dmn > 0.0 ? slim : 0.0;
+}
+
+MXD double slope2(const double* S, int I, int lo, int hi, bool lobc, bool hibc) {
+    // MaestroSlopes.cpp:43-90
+    const double sm1 = S[1], s0 = S[2], sp1 = S[3];
+    double del = 0.5 * (sp1 - sm1);
+    const double dpls = 2.0 * (sp1 - s0);
+    const double dmn = 2.0 * (s0 - sm1);
+    const double slim = mc_lim(dpls, dmn);
+    double r = signed_mag(dmin_(slim, fabs(del)), del);
+    if (lobc) {
+        if (I == lo - 1) {
+            r = 0.0;
+        } else if (I == lo) {
+            del = div3(sp1 + 3.0 * s0 - 4.0 * sm1);
+            r = signed_mag(dmin_(slim, fabs(del)), del);
+        }
+    }
+    if (hibc) {
+        if (I == hi + 1) {
+            r = 0.0;
+        } else if (I == hi) {
+            del = -div3(sm1 + 3.0 * s0 - 4.0 * sp1);
+            r = signed_mag(dmin_(slim, fabs(del)), del);
+        }
+    }
+    return r;
+}
+
+MXD double slope4(const double* S, int I, int lo, int hi, bool lobc, bool hibc, bool xquirk) {
+    // MaestroSlopes.cpp:95-201
+    const double sm2 = S[0], sm1 = S[1], s0 = S[2], sp1 = S[3], sp2 = S[4];
+    // left
+    double dcen = 0.5 * (s0 - sm2);
+    double dmn = 2.0 * (sm1 - sm2);
+    double dpls = 2.0 * (s0 - sm1);
+    double dlim = mc_lim(dpls, dmn);
+    double dxl = signed_mag(dmin_(dlim, fabs(dcen)), dcen);
+    // right
+    dcen = 0.5 * (sp2 - s0);
+    dmn = 2.0 * (sp1 - s0);
+    dpls = 2.0 * (sp2 - sp1);
+    dlim = mc_lim(dpls, dmn);
+    double dxr = signed_mag(dmin_(dlim, fabs(dcen)), dcen);
+    // centre
+    dcen = 0.5 * (sp1 - sm1);
+    dmn = 2.0 * (s0 - sm1);
+    dpls = 2.0 * (sp1 - s0);
+    dlim = mc_lim(dpls, dmn);
+    double ds = 4.0 / 3.0 * dcen - div6(dxr + dxl);
+    double r = signed_mag(dmin_(fabs(ds), dlim), dcen);
+
+    if (lobc || hibc) {
+        // one-sided rows.  QUIRK (MaestroSlopes.cpp:142,156,178,192 vs :341.. and :539..):
+        // Slopex keeps the centred `dlim` where Slopey/z use the freshly computed `slim`.
+        if (lobc) {
+            if (I == lo - 1) {
+                r = 0.0;
+            } else if (I == lo) {
+                const double del = -16.0 / 15.0 * sm1 + 0.5 * s0 + 2.0 / 3.0 * sp1 - 0.1 * sp2;
+                const double a = 2.0 * (s0 - sm1), b = 2.0 * (sp1 - s0);
+                double slim = dmin_(fabs(b), fabs(a));
+                slim = b * a > 0.0 ? (xquirk ? dlim : slim) : 0.0;
+                r = signed_mag(dmin_(slim, fabs(del)), del);
+            } else if (I == lo + 1) {
+                const double del = -16.0 / 15.0 * sm2 + 0.5 * sm1 + 2.0 / 3.0 * s0 - 0.1 * sp1;
+                const double a = 2.0 * (sm1 - sm2), b = 2.0 * (s0 - sm1);
+                double slim = dmin_(fabs(b), fabs(a));
+                slim = b * a > 0.0 ? (xquirk ? dlim : slim) : 0.0;
+                dxl = signed_mag(dmin_(slim, fabs(del)), del);
+                ds = 4.0 / 3.0 * dcen - div6(dxr + dxl);
+                r = signed_mag(dmin_(fabs(ds), dlim), dcen);
+            }
+        }
+        if (hibc) {
+            if (I == hi + 1) {
+                r = 0.0;
+            } else if (I == hi) {
+                const double del = -(-16.0 / 15.0 * sp1 + 0.5 * s0 + 2.0 / 3.0 * sm1 - 0.1 * sm2);
+                const double a = 2.0 * (s0 - sm1), b = 2.0 * (sp1 - s0);
+                double slim = dmin_(fabs(b), fabs(a));
+                slim = b * a > 0.0 ? (xquirk ? dlim : slim) : 0.0;
+                r = signed_mag(dmin_(slim, fabs(del)), del);
+            } else if (I == hi - 1) {
+                const double del = -(-16.0 / 15.0 * sp2 + 0.5 * sp1 + 2.0 / 3.0 * s0 - 0.1 * sm1);
+                const double a = 2.0 * (sp1 - s0), b = 2.0 * (sp2 - sp1);
+                double slim = dmin_(fabs(b), fabs(a));
+                slim = b * a > 0.0 ? (xquirk ? dlim : slim) : 0.0;
+                dxr = signed_mag(dmin_(slim, fabs(del)), del);
+                ds = 4.0 / 3.0 * dcen - div6(dxl + dxr);
+                r = signed_mag(dmin_(fabs(ds), dlim), dcen);
+            }
+        }
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// PPM: Source/MaestroPPM.cpp
+// ---------------------------------------------------------------------------------------
+// van Leer slope from the two one-sided differences dm = s0 - sm1, dp = sp1 - s0 and the
+// centred one dc2 = sp1 - sm1 (MaestroPPM.cpp:42-49)
+MXD double vanleer(double sm1, double s0, double sp1) {
+    const double dsc = 0.5 * (sp1 - sm1);
+    const double dsl = 2.0 * (s0 - sm1);
+    const double dsr = 2.0 * (sp1 - s0);
+    const double m = dmin_(fabs(dsc), dmin_(fabs(dsl), fabs(dsr)));
+    return (dsl * dsr > 0.0) ? signed_mag(m, dsc) : 0.0;
+}
+
+// 4th-order edge between sL and sR with van Leer slopes dL, dR, clamped (MaestroPPM.cpp:62-67)
+MXD double vl_edge(double sL, double sR, double dL, double dR) {
+    double e = 0.5 * (sR + sL) - div6(dR - dL);
+    e = dmax_(e, dmin_(sR, sL));
+    e = dmin_(e, dmax_(sR, sL));
+    return e;
+}
+
+MXD void cw_limit(double s0, double& sm, double& sp) {
+    // MaestroPPM.cpp:106-115
+    const double dp = sp - s0, dm = sm - s0;
+    if (dp * (s0 - sm) <= 0.0) {
+        sp = s0;
+        sm = s0;
+    } else if (fabs(dp) >= 2.0 * fabs(dm)) {
+        sp = 3.0 * s0 - 2.0 * sm;
+    } else if (fabs(dm) >= 2.0 * fabs(dp)) {
+        sm = 3.0 * s0 - 2.0 * sp;
+    }
+}
+
+MXD double bc_edge(double a, double b, double c, double d, double m0, double m1) {
+    // MaestroPPM.cpp:124-131
+    double v = -0.2 * a + 0.75 * b + 0.5 * c - 0.05 * d;
+    v = dmax_(v, dmin_(m0, m1));
+    v = dmin_(v, dmax_(m0, m1));
+    return v;
+}
+
+// ppm_type 1: sm, sp of the limited parabola in the cell.  S[o+3], o in [-3,3] (only -2..2
+// read).  MaestroPPM.cpp:34-205.
+template <bool BC>
+MXD void ppm1_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, double& sm,
+                       double& sp) {
+    const double sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
+    const double dl = vanleer(sm2, sm1, s0);
+    const double dc = vanleer(sm1, s0, sp1);
+    const double dr = vanleer(s0, sp1, sp2);
+    sm = vl_edge(sm1, s0, dl, dc);
+    sp = vl_edge(s0, sp1, dc, dr);
+    const double sedgel = sp, sedger = sm;
+    cw_limit(s0, sm, sp);
+    if (BC) {
+        if (I == lo) {
+            if (lobc) {
+                sm = sm1;
+                sp = bc_edge(sm1, s0, sp1, sp2, sp1, s0);
+            }
+        } else if (I == lo + 1) {
+            if (lobc) {
+                sm = bc_edge(sm2, sm1, s0, sp1, s0, sm1);
+                sp = sedgel;
+                cw_limit(s0, sm, sp);
+            }
+        } else if (I == hi) {
+            if (hibc) {
+                sp = sp1;
+                sm = bc_edge(sp1, s0, sm1, sm2, sm1, s0);
+            }
+        } else if (I == hi - 1) {
+            if (hibc) {
+                sp = bc_edge(sp2, sp1, s0, sm1, s0, sp1);
+                sm = sedger;
+                cw_limit(s0, sm, sp);
+            }
+        }
+    }
+}
+
+// ppm_type 2 edge (MaestroPPM.cpp:258-279): a,b,c,d = the four cells around the edge b|c
+MXD double cs_edge(double a, double b, double c, double d) {
+    const double C = 1.25;
+    double e = (7.0 / 12.0) * (b + c) - (1.0 / 12.0) * (a + d);
+    if ((e - b) * (c - e) < 0.0) {
+        const double D2 = 3.0 * (b - 2.0 * e + c);
+        const double D2L = a - 2.0 * b + c;
+        const double D2R = b - 2.0 * c + d;
+        const double sgn = sign1(D2);
+        const double D2LIM = sgn * dmax_(dmin_(C * sgn * D2L, dmin_(C * sgn * D2R, sgn * D2)), 0.0);
+        e = 0.5 * (b + c) - div6(D2LIM);
+    }
+    return e;
+}
+
+// Colella-Sekora limiter (MaestroPPM.cpp:356-441)
+MXD void cs_limit(double sedgel, double sedge, double sedger, double sedgerr, double sm2,
+                  double sm1, double s0, double sp1, double sp2, double bigm_thresh, double& sm,
+                  double& sp) {
+    const double C = 1.25;
+    double alphap = sedger - s0;
+    double alpham = sedge - s0;
+    const bool bigp = fabs(alphap) > 2.0 * fabs(alpham);
+    const bool bigm = fabs(alpham) > 2.0 * fabs(alphap);
+    bool extremum = false;
+    if (alpham * alphap >= 0.0) {
+        extremum = true;
+    } else if (bigp || bigm) {
+        const double dafacem = sedge - sedgel;
+        const double dafacep = sedgerr - sedger;
+        const double dabarm = s0 - sm1;
+        const double dabarp = sp1 - s0;
+        const double dafacemin = dmin_(fabs(dafacem), fabs(dafacep));
+        const double dabarmin = dmin_(fabs(dabarm), fabs(dabarp));
+        double dachkm, dachkp;
+        if (dafacemin >= dabarmin) {
+            dachkm = dafacem;
+            dachkp = dafacep;
+        } else {
+            dachkm = dabarm;
+            dachkp = dabarp;
+        }
+        extremum = (dachkm * dachkp <= 0.0);
+    }
+    if (extremum) {
+        const double D2 = 6.0 * (alpham + alphap);
+        const double D2L = sm2 - 2.0 * sm1 + s0;
+        const double D2R = s0 - 2.0 * sp1 + sp2;
+        const double D2C = sm1 - 2.0 * s0 + sp1;
+        const double sgn = sign1(D2);
+        const double D2LIM = dmax_(
+            dmin_(sgn * D2, dmin_(C * sgn * D2L, dmin_(C * sgn * D2R, C * sgn * D2C))), 0.0);
+        const double D2ABS = dmax_(fabs(D2), 1.e-10);
+        alpham = alpham * D2LIM / D2ABS;
+        alphap = alphap * D2LIM / D2ABS;
+    } else {
+        if (bigp) {
+            const double sgn = sign1(alpham);
+            const double amax = -alphap * alphap / (4.0 * (alpham + alphap));
+            const double delam = sm1 - s0;
+            if (sgn * amax >= sgn * delam) {
+                if (sgn * (delam - alpham) >= 1.e-10) {
+                    alphap = (-2.0 * delam - 2.0 * sgn * sqrt(delam * delam - delam * alpham));
+                } else {
+                    alphap = -2.0 * alpham;
+                }
+            }
+        }
+        if (bigm) {
+            const double sgn = sign1(alphap);
+            const double amax = -alpham * alpham / (4.0 * (alpham + alphap));
+            const double delap = sp1 - s0;
+            if (sgn * amax >= sgn * delap) {
+                if (sgn * (delap - alphap) >= bigm_thresh) {
+                    alpham = (-2.0 * delap - 2.0 * sgn * sqrt(delap * delap - delap * alphap));
+                } else {
+                    alpham = -2.0 * alphap;
+                }
+            }
+        }
+    }
+    sm = s0 + alpham;
+    sp = s0 + alphap;
+}
+
+// ppm_type 2 parabola: S[o+3], o in [-3,3].  MaestroPPM.cpp:255-719.
+template <bool BC>
+MXD void ppm2_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, bool xquirk,
+                       double& sm, double& sp) {
+    const double sm3 = S[0], sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5],
+                 sp3 = S[6];
+    double sedgel = cs_edge(sm3, sm2, sm1, s0);
+    double sedge = cs_edge(sm2, sm1, s0, sp1);
+    double sedger = cs_edge(sm1, s0, sp1, sp2);
+    double sedgerr = cs_edge(s0, sp1, sp2, sp3);
+    cs_limit(sedgel, sedge, sedger, sedgerr, sm2, sm1, s0, sp1, sp2, 1.e-10, sm, sp);
+    if (BC) {
+        if (lobc) {
+            if (I == lo) {
+                sm = sm1;
+                sp = bc_edge(sm1, s0, sp1, sp2, sp1, s0);
+            } else if (I == lo + 1) {
+                sedgel = sm2;
+                sedge = bc_edge(sm2, sm1, s0, sp1, s0, sm1);
+            } else if (I == lo + 2) {
+                sedgel = bc_edge(sm3, sm2, sm1, s0, sm1, sm2);
+            }
+            if (I == lo + 1 || I == lo + 2) {
+                // QUIRK: x-direction lo side tests 1.e10 (MaestroPPM.cpp:566), y/z 1.e-10
+                cs_limit(sedgel, sedge, sedger, sedgerr, sm2, sm1, s0, sp1, sp2,
+                         xquirk ? 1.e10 : 1.e-10, sm, sp);
+            }
+        }
+        if (hibc) {
+            if (I == hi) {
+                sp = sp1;
+                sm = bc_edge(sp1, s0, sm1, sm2, sm1, s0);
+            } else if (I == hi - 1) {
+                // QUIRK: y and z reset sedgerr = s(+2) (MaestroPPM.cpp:1343,:2087), x does not
+                if (!xquirk) sedgerr = sp2;
+                sedger = bc_edge(sp2, sp1, s0, sm1, s0, sp1);
+            } else if (I == hi - 2) {
+                sedgerr = bc_edge(sp3, sp2, sp1, s0, sp1, sp2);
+            }
+            if (I == hi - 1 || I == hi - 2) {
+                cs_limit(sedgel, sedge, sedger, sedgerr, sm2, sm1, s0, sp1, sp2, 1.e-10, sm, sp);
+            }
+        }
+    }
+}
+
+// characteristic integration, MaestroPPM.cpp:210-231 (is_umac).  sig = |u| dt / h already
+// formed per face by the caller ((|u| * dt) / h, IEEE division).
+MXD double ppm_Ip(double sm, double sp, double s0, double s6, double up, double sig_p, double eps) {
+    return (up > eps) ? sp - 0.5 * sig_p * (sp - sm - (1.0 - 2.0 / 3.0 * sig_p) * s6) : s0;
+}
+MXD double ppm_Im(double sm, double sp, double s0, double s6, double um, double sig_m, double eps) {
+    return (um < -eps) ? sm + 0.5 * sig_m * (sp - sm + (1.0 - 2.0 / 3.0 * sig_m) * s6) : s0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Riemann / BC helpers of MakeEdgeScalPredictor / Transverse / Edges
+// ---------------------------------------------------------------------------------------
+MXD double upwind(double u, double eps, double sl, double sr) {
+    // MaestroMakeEdgeScalars.cpp:745-748
+    const double r = (u > 0.0) ? sl : sr;
+    return (fabs(u) > eps) ? r : 0.5 * (sl + sr);
+}
+
+// :710-742 and the identical blocks in the transverse stage
+MXD void bc_pair(int I, int lo, int hi, int bclo, int bchi, bool velclamp, double s_lo,
+                 double s_hi, double& sl, double& sr) {
+    if (I == lo) {
+        if (bclo == BC_EXT_DIR) {
+            sl = s_lo;
+            sr = s_lo;
+        } else if (bclo == BC_FOEXTRAP || bclo == BC_HOEXTRAP) {
+            if (velclamp) sr = dmin_(sr, 0.0);
+            sl = sr;
+        } else if (bclo == BC_REFLECT_EVEN) {
+            sl = sr;
+        } else if (bclo == BC_REFLECT_ODD) {
+            sl = 0.0;
+            sr = 0.0;
+        }
+    } else if (I == hi + 1) {
+        if (bchi == BC_EXT_DIR) {
+            sl = s_hi;
+            sr = s_hi;
+        } else if (bchi == BC_FOEXTRAP || bchi == BC_HOEXTRAP) {
+            if (velclamp) sl = dmax_(sl, 0.0);
+            sr = sl;
+        } else if (bchi == BC_REFLECT_EVEN) {
+            sr = sl;
+        } else if (bchi == BC_REFLECT_ODD) {
+            sl = 0.0;
+            sr = 0.0;
+        }
+    }
+}
+
+// :1455-1485
+MXD double bc_final(int I, int lo, int hi, int bclo, int bchi, bool velclamp, double s_lo,
+                    double s_hi, double el, double er, double val) {
+    if (I == lo) {
+        if (bclo == BC_EXT_DIR) {
+            val = s_lo;
+        } else if (bclo == BC_FOEXTRAP || bclo == BC_HOEXTRAP) {
+            val = velclamp ? dmin_(er, 0.0) : er;
+        } else if (bclo == BC_REFLECT_EVEN) {
+            val = er;
+        } else if (bclo == BC_REFLECT_ODD) {
+            val = 0.0;
+        }
+    } else if (I == hi + 1) {
+        if (bchi == BC_EXT_DIR) {
+            val = s_hi;
+        } else if (bchi == BC_FOEXTRAP || bchi == BC_HOEXTRAP) {
+            val = velclamp ? dmax_(el, 0.0) : el;
+        } else if (bchi == BC_REFLECT_EVEN) {
+            val = el;
+        } else if (bchi == BC_REFLECT_ODD) {
+            val = 0.0;
+        }
+    }
+    return val;
+}
+
+}  // namespace mxd
+#endif
