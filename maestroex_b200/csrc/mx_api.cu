@@ -268,9 +268,10 @@ int run_edge(Session& S, const KGeom& kg, const MxEdgeParams* p, const EdgeArgs&
     KEdge e = make_kedge(p);
     if (p->num_comp == 0) return MX_OK;
     if (fused_edge_supported(kg, e)) {
-        return fused_edge_scal(kg, e, p, a.state, a.sedge, a.umac, a.force, S.stream()) == 0
-                   ? MX_OK
-                   : fail(MX_ERR_CUDA, "fused edge kernel launch failed");
+        // > 0: a BC code the fused kernel does not carry (ext_dir): use the staged kernels
+        const int rc = fused_edge_scal(kg, e, p, a.state, a.sedge, a.umac, a.force, S.stream());
+        if (rc == 0) return MX_OK;
+        if (rc < 0) return fail(MX_ERR_CUDA, "fused edge kernel launch failed");
     }
     void* scratch = nullptr;
     CUDA_OK(S.alloc(&scratch, sizeof(double) * staged_scratch_doubles(kg)));
@@ -566,10 +567,10 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
     }
     KEdge e = make_kedge(epar);
     if (fused_density_supported(kg, e, f)) {
-        if (fused_density(kg, e, epar, rho_bccomp, f, a.state, a.sedge, sf, eta, a.umac, a.force,
-                          mac, S.stream()) != 0)
-            return fail(MX_ERR_CUDA, "fused density kernel launch failed");
-        return S.finish();
+        const int rc = fused_density(kg, e, epar, rho_bccomp, f, a.state, a.sedge, sf, eta, a.umac,
+                                     a.force, mac, S.stream());
+        if (rc == 0) return S.finish();
+        if (rc < 0) return fail(MX_ERR_CUDA, "fused density kernel launch failed");
     }
     // composition of the three reference calls (MaestroDensityAdvance.cpp:115,128,182)
     MX_TRY(run_edge(S, kg, epar, a));
@@ -621,6 +622,13 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
         MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
         MX_TRY(S.fab(&sflux[d], &sf[d], fpar->rhoh_comp, 1, true, true));
         MX_TRY(S.upload(&sedge[d], a.sedge[d], fpar->rho_comp, 1));
+    }
+    KEdge e = make_kedge(epar);
+    if (fused_enthalpy_supported(kg, e, f)) {
+        const int rc =
+            fused_enthalpy(kg, e, epar, f, a.state, a.sedge, sf, a.umac, a.force, S.stream());
+        if (rc == 0) return S.finish();
+        if (rc < 0) return fail(MX_ERR_CUDA, "fused enthalpy kernel launch failed");
     }
     MX_TRY(run_edge(S, kg, epar, a));
     flux_rhoh(kg, f, sf, a.sedge, a.umac, mac, S.stream());

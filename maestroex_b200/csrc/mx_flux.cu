@@ -6,6 +6,7 @@
 #include "mx_common.h"
 #include "mx_device.cuh"
 #include "mx_flux.h"
+#include "mx_fluxdev.cuh"
 
 namespace {
 
@@ -95,31 +96,9 @@ __global__ void k_rhoh(KGeom g, KFlux f, int d, DFab sflux, DFab sedge, DFab uma
     double* F = sflux.comp(f.rhoh) + fo;
     const bool sph = g.dim == 3 && f.spherical;
     if (!sph) {
-        if (have_h) {
-            const double ser = sedge.comp(f.rho)[so];
-            if (spt == MX_PRED_RHOPRIME_AND_X) {
-                const double rho0_edge =
-                    (d == vert) ? 0.5 * (f.rho0_edge_old[r * f.st_rho0_edge_old] +
-                                         f.rho0_edge_new[r * f.st_rho0_edge_new])
-                                : 0.5 * (f.rho0_old[r * f.st_rho0_old] +
-                                         f.rho0_new[r * f.st_rho0_new]);
-                *F = u * (rho0_edge + ser) * seh;
-            } else if (spt == MX_PRED_RHO_AND_X || spt == MX_PRED_RHOX) {
-                *F = u * ser * seh;
-            }
-        } else if (have_rhoh) {
-            *F = u * seh;
-        } else if (ept == MX_PRED_RHOHPRIME || ept == MX_PRED_T_THEN_RHOHPRIME) {
-            if (d == vert) {
-                const double rhoh0_edge = 0.5 * (f.rhoh0_edge_old[r * f.st_rhoh0_edge_old] +
-                                                 f.rhoh0_edge_new[r * f.st_rhoh0_edge_new]);
-                *F = u * (seh + rhoh0_edge);  // :782-784
-            } else {
-                const double rhoh0_edge =
-                    0.5 * (f.rhoh0_old[r * f.st_rhoh0_old] + f.rhoh0_new[r * f.st_rhoh0_new]);
-                *F = u * (rhoh0_edge + seh);  // :706-708
-            }
-        }
+        const double ser = mxd::needs_sedge_rho_for_rhoh(f) ? sedge.comp(f.rho)[so] : 0.0;
+        double Fv;
+        if (mxd::rhoh_flux_planar(f, d == vert, r, u, ser, seh, &Fv)) *F = Fv;
     } else if (f.exact) {
         // QUIRK: x-face tests `have_h || have_rhoh` (:797); y/z `have_h || have_hprime`
         const bool skip = (d == 0) ? (have_h || have_rhoh) : (have_h || have_hprime);

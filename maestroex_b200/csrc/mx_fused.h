@@ -12,4 +12,8 @@ int fused_density(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, int 
                   const KFlux& f, const DFab& state, const DFab* sedge, const DFab* sflux,
                   const DFab& etarho, const DFab* umac, const DFab& force, const KMac& mac,
                   cudaStream_t stream);
+bool fused_enthalpy_supported(const KGeom& g, const KEdge& e, const KFlux& f);
+int fused_enthalpy(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, const KFlux& f,
+                   const DFab& state, const DFab* sedge, const DFab* sflux, const DFab* umac,
+                   const DFab& force, cudaStream_t stream);
 #endif

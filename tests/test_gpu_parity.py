@@ -205,3 +205,28 @@ def test_fused_enthalpy_pass(mx, oracle_calls, ppm, ept, cons):
     ge, gf = to_host(ge), to_host(gf)
     compare_faces(ge, want_e, [RHO, RHOH], "fused sedge", TOL)
     compare_faces(gf, want_f, [RHOH], "fused rhoh flux", TOL)
+
+
+@pytest.mark.parametrize("zchunk", ["1", "5", "16", "1000"])
+@pytest.mark.parametrize("ppm", [0, 1, 2])
+def test_fused_zchunk_independence(mx, oracle_calls, ppm, zchunk, monkeypatch):
+    """The z-chunk size of the streaming kernel must not change a single bit."""
+    from gpu_util import to_device, to_host
+    monkeypatch.setenv("MXADV_ZCHUNK", zchunk)
+    ng = 4 if ppm == 2 else 3
+    prob = make_problem(dim=3, n=(35, 29, 23), nspec=2, ng=ng, bc_kind="reacting_bubble", seed=41)
+    par = prob.edge_params(RHO, prob.nscal, ppm_type=ppm)
+    want = run_edge(oracle_calls, prob, par)
+    got = to_host(run_edge(mx, to_device(prob), par))
+    compare_faces(got, want, list(range(prob.nscal)), f"sedge zchunk={zchunk}", TOL)
+
+
+def test_staged_and_fused_agree(mx, oracle_calls, monkeypatch):
+    """MXADV_FORCE_STAGED routes the same call through the general kernels."""
+    from gpu_util import to_device, to_host
+    prob = make_problem(dim=3, n=(40, 20, 18), nspec=3, ng=3, bc_kind="reacting_bubble", seed=42)
+    par = prob.edge_params(RHO, prob.nscal, ppm_type=1)
+    fused = to_host(run_edge(mx, to_device(prob), par))
+    monkeypatch.setenv("MXADV_FORCE_STAGED", "1")
+    staged = to_host(run_edge(mx, to_device(prob), par))
+    compare_faces(fused, staged, list(range(prob.nscal)), "fused vs staged", TOL)
