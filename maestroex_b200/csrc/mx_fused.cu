@@ -157,6 +157,10 @@ __global__ void __launch_bounds__(GX* GY, 1) k_fused(const __grid_constant__ Fus
     const bool vyj = inG && ty >= 1 && j <= thy;
     const bool fx = inG && tx >= 1;  // thread owns the x-face between (i-1,j) and (i,j)
     const bool fy = inG && ty >= 1;
+    // faces this block stores: the tile's low faces, plus the high face only on the last tile
+    // (the neighbouring tile owns it otherwise; sflux(Rho) is accumulated, so no double owner)
+    const bool ownx = fx && vyj && (i <= thx || thx == g.vhi[0]);
+    const bool owny = fy && vxi && (j <= thy || thy == g.vhi[1]);
     const int rc = (ty + LA) * PW + (tx + LA);  // own cell inside a ring plane
 
     const DFab& st = A.state;
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(GX* GY, 1) k_fused(const __grid_constant__ Fus
             // ---- phase 6: final edge states (+ fluxes) ---------------------------------
             if (a >= k0 + 1) {
                 const int p = a - 1;
-                if (fx && vyj) {
+                if (ownx) {
                     const double el = ((slx_p - QX1[tid - 1]) - QX2[tid - 1]) + FS[tid - 1];
                     const double er = ((srx_p - t4yz) - t4zy) + fs_prev;
                     double val = upwind(uf_p, A.eps, el, er);
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(GX* GY, 1) k_fused(const __grid_constant__ Fus
                             F.comp(comp)[F.off(i, j, p)] = fl;
                     }
                 }
-                if (fy && vxi) {
+                if (owny) {
                     const double el = ((sly_p - QY1[tid - GX]) - QY2[tid - GX]) + FS[tid - GX];
                     const double er = ((sry_p - t4xz) - t4zx) + fs_prev;
                     double val = upwind(vf_p, A.eps, el, er);
