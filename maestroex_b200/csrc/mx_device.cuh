@@ -200,17 +200,14 @@ MXD double bc_edge(double a, double b, double c, double d, double m0, double m1)
     return v;
 }
 
-// ppm_type 1: sm, sp of the limited parabola in the cell.  S[o+3], o in [-3,3] (only -2..2
-// read).  MaestroPPM.cpp:34-205.
+// ppm_type 1, second half: CW84 limiter + BC rows applied to the unlimited edge values
+// sm_u = edge(i-1/2), sp_u = edge(i+1/2) (MaestroPPM.cpp:100-205).  S[o+3], o in [-2,2] read.
 template <bool BC>
-MXD void ppm1_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, double& sm,
-                       double& sp) {
+MXD void ppm1_finish(const double* S, int I, int lo, int hi, bool lobc, bool hibc, double sm_u,
+                     double sp_u, double& sm, double& sp) {
     const double sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
-    const double dl = vanleer(sm2, sm1, s0);
-    const double dc = vanleer(sm1, s0, sp1);
-    const double dr = vanleer(s0, sp1, sp2);
-    sm = vl_edge(sm1, s0, dl, dc);
-    sp = vl_edge(s0, sp1, dc, dr);
+    sm = sm_u;
+    sp = sp_u;
     const double sedgel = sp, sedger = sm;
     cw_limit(s0, sm, sp);
     if (BC) {
@@ -238,6 +235,19 @@ MXD void ppm1_parabola(const double* S, int I, int lo, int hi, bool lobc, bool h
             }
         }
     }
+}
+
+// ppm_type 1: sm, sp of the limited parabola in the cell.  S[o+3], o in [-3,3] (only -2..2
+// read).  MaestroPPM.cpp:34-205.
+template <bool BC>
+MXD void ppm1_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, double& sm,
+                       double& sp) {
+    const double sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
+    const double dl = vanleer(sm2, sm1, s0);
+    const double dc = vanleer(sm1, s0, sp1);
+    const double dr = vanleer(s0, sp1, sp2);
+    ppm1_finish<BC>(S, I, lo, hi, lobc, hibc, vl_edge(sm1, s0, dl, dc), vl_edge(s0, sp1, dc, dr),
+                    sm, sp);
 }
 
 // ppm_type 2 edge (MaestroPPM.cpp:258-279): a,b,c,d = the four cells around the edge b|c
@@ -325,16 +335,14 @@ MXD void cs_limit(double sedgel, double sedge, double sedger, double sedgerr, do
     sp = s0 + alphap;
 }
 
-// ppm_type 2 parabola: S[o+3], o in [-3,3].  MaestroPPM.cpp:255-719.
+// ppm_type 2, second half: limiter + BC rows given the four unlimited edges around the cell
+// (sedgel = edge(i-3/2) .. sedgerr = edge(i+3/2)).  MaestroPPM.cpp:356-719.
 template <bool BC>
-MXD void ppm2_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, bool xquirk,
-                       double& sm, double& sp) {
+MXD void ppm2_finish(const double* S, int I, int lo, int hi, bool lobc, bool hibc, bool xquirk,
+                     double sedgel, double sedge, double sedger, double sedgerr, double& sm,
+                     double& sp) {
     const double sm3 = S[0], sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5],
                  sp3 = S[6];
-    double sedgel = cs_edge(sm3, sm2, sm1, s0);
-    double sedge = cs_edge(sm2, sm1, s0, sp1);
-    double sedger = cs_edge(sm1, s0, sp1, sp2);
-    double sedgerr = cs_edge(s0, sp1, sp2, sp3);
     cs_limit(sedgel, sedge, sedger, sedgerr, sm2, sm1, s0, sp1, sp2, 1.e-10, sm, sp);
     if (BC) {
         if (lobc) {
@@ -371,6 +379,17 @@ MXD void ppm2_parabola(const double* S, int I, int lo, int hi, bool lobc, bool h
     }
 }
 
+// ppm_type 2 parabola: S[o+3], o in [-3,3].  MaestroPPM.cpp:255-719.
+template <bool BC>
+MXD void ppm2_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, bool xquirk,
+                       double& sm, double& sp) {
+    const double sm3 = S[0], sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5],
+                 sp3 = S[6];
+    ppm2_finish<BC>(S, I, lo, hi, lobc, hibc, xquirk, cs_edge(sm3, sm2, sm1, s0),
+                    cs_edge(sm2, sm1, s0, sp1), cs_edge(sm1, s0, sp1, sp2),
+                    cs_edge(s0, sp1, sp2, sp3), sm, sp);
+}
+
 // characteristic integration, MaestroPPM.cpp:210-231 (is_umac).  sig = |u| dt / h already
 // formed per face by the caller ((|u| * dt) / h, IEEE division).
 MXD double ppm_Ip(double sm, double sp, double s0, double s6, double up, double sig_p, double eps) {
@@ -387,6 +406,18 @@ MXD double upwind(double u, double eps, double sl, double sr) {
     // MaestroMakeEdgeScalars.cpp:745-748
     const double r = (u > 0.0) ? sl : sr;
     return (fabs(u) > eps) ? r : 0.5 * (sl + sr);
+}
+
+// the same Riemann choice with the velocity predicates formed once per face: pos = u > 0,
+// nz = |u| > eps; `slow` is a warp-uniform "some lane of this warp has !nz" flag, so the
+// averaging arm costs nothing where the flow is nowhere stagnant
+MXD double upw(bool pos, bool nz, bool slow, double sl, double sr) {
+    double r = pos ? sl : sr;
+    if (slow) {
+        const double avg = 0.5 * (sl + sr);
+        r = nz ? r : avg;
+    }
+    return r;
 }
 
 // :710-742 and the identical blocks in the transverse stage
