@@ -158,6 +158,13 @@ MXD double slope4(const double* S, int I, int lo, int hi, bool lobc, bool hibc, 
     return r;
 }
 
+MXD double slope_any(int order, const double* S, int I, int lo, int hi, bool lobc, bool hibc,
+                     bool xquirk) {
+    if (order == 0) return 0.0;
+    if (order == 2) return slope2(S, I, lo, hi, lobc, hibc);
+    return slope4(S, I, lo, hi, lobc, hibc, xquirk);
+}
+
 // ---------------------------------------------------------------------------------------
 // PPM: Source/MaestroPPM.cpp
 // ---------------------------------------------------------------------------------------
@@ -168,7 +175,8 @@ MXD double vanleer(double sm1, double s0, double sp1) {
     const double dsl = 2.0 * (s0 - sm1);
     const double dsr = 2.0 * (sp1 - s0);
     const double m = dmin_(fabs(dsc), dmin_(fabs(dsl), fabs(dsr)));
-    return (dsl * dsr > 0.0) ? signed_mag(m, dsc) : 0.0;
+    const double r = signed_mag(m, dsc);
+    return (dsl * dsr > 0.0) ? r : 0.0;
 }
 
 // 4th-order edge between sL and sR with van Leer slopes dL, dR, clamped (MaestroPPM.cpp:62-67)
@@ -180,16 +188,18 @@ MXD double vl_edge(double sL, double sR, double dL, double dR) {
 }
 
 MXD void cw_limit(double s0, double& sm, double& sp) {
-    // MaestroPPM.cpp:106-115
+    // MaestroPPM.cpp:106-115, written with selects (both arms are cheap and side-effect free)
     const double dp = sp - s0, dm = sm - s0;
-    if (dp * (s0 - sm) <= 0.0) {
-        sp = s0;
-        sm = s0;
-    } else if (fabs(dp) >= 2.0 * fabs(dm)) {
-        sp = 3.0 * s0 - 2.0 * sm;
-    } else if (fabs(dm) >= 2.0 * fabs(dp)) {
-        sm = 3.0 * s0 - 2.0 * sp;
-    }
+    const bool flat = dp * (s0 - sm) <= 0.0;
+    const bool c1 = fabs(dp) >= 2.0 * fabs(dm);
+    const bool c2 = fabs(dm) >= 2.0 * fabs(dp);
+    const double s3 = 3.0 * s0;
+    const double sp_c1 = s3 - 2.0 * sm;
+    const double sm_c2 = s3 - 2.0 * sp;
+    const double sp_n = c1 ? sp_c1 : sp;
+    const double sm_n = (!c1 && c2) ? sm_c2 : sm;
+    sp = flat ? s0 : sp_n;
+    sm = flat ? s0 : sm_n;
 }
 
 MXD double bc_edge(double a, double b, double c, double d, double m0, double m1) {
@@ -393,10 +403,12 @@ MXD void ppm2_parabola(const double* S, int I, int lo, int hi, bool lobc, bool h
 // characteristic integration, MaestroPPM.cpp:210-231 (is_umac).  sig = |u| dt / h already
 // formed per face by the caller ((|u| * dt) / h, IEEE division).
 MXD double ppm_Ip(double sm, double sp, double s0, double s6, double up, double sig_p, double eps) {
-    return (up > eps) ? sp - 0.5 * sig_p * (sp - sm - (1.0 - 2.0 / 3.0 * sig_p) * s6) : s0;
+    const double v = sp - 0.5 * sig_p * (sp - sm - (1.0 - 2.0 / 3.0 * sig_p) * s6);
+    return (up > eps) ? v : s0;
 }
 MXD double ppm_Im(double sm, double sp, double s0, double s6, double um, double sig_m, double eps) {
-    return (um < -eps) ? sm + 0.5 * sig_m * (sp - sm + (1.0 - 2.0 / 3.0 * sig_m) * s6) : s0;
+    const double v = sm + 0.5 * sig_m * (sp - sm + (1.0 - 2.0 / 3.0 * sig_m) * s6);
+    return (um < -eps) ? v : s0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -59,6 +59,34 @@ __device__ __forceinline__ bool rhoh_flux_planar(const KFlux& f, bool vertical, 
     return false;
 }
 
+// the same with the time-centred base-state values already formed (per-plane tables of the
+// streaming kernel): rho0e = 0.5 (rho0[_edge]_old + rho0[_edge]_new), rhoh0e likewise
+__device__ __forceinline__ bool rhoh_flux_tab(const KFlux& f, bool have_h, double u, double ser,
+                                              double seh, double rho0e, double rhoh0e,
+                                              bool vertical, double* F) {
+    const int ept = f.ept, spt = f.spt;
+    if (have_h) {
+        if (spt == MX_PRED_RHOPRIME_AND_X) {
+            *F = u * (rho0e + ser) * seh;
+            return true;
+        }
+        if (spt == MX_PRED_RHO_AND_X || spt == MX_PRED_RHOX) {
+            *F = u * ser * seh;
+            return true;
+        }
+        return false;
+    }
+    if (ept == MX_PRED_RHOH) {
+        *F = u * seh;
+        return true;
+    }
+    if (ept == MX_PRED_RHOHPRIME || ept == MX_PRED_T_THEN_RHOHPRIME) {
+        *F = vertical ? u * (seh + rhoh0e) : u * (rhoh0e + seh);
+        return true;
+    }
+    return false;
+}
+
 __device__ __forceinline__ bool needs_sedge_rho_for_rhoh(const KFlux& f) {
     return f.ept == MX_PRED_H || f.ept == MX_PRED_T_THEN_H || f.ept == MX_PRED_TPRIME_THEN_H;
 }

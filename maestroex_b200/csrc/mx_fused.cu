@@ -496,508 +496,7 @@ __global__ void __launch_bounds__(GX* GY, 1) k_fused(const __grid_constant__ Fus
 }
 
 
-// =========================================================================================
-// v2 streaming kernel.  Same decomposition and the same arithmetic as k_fused above, but
-//  * the z-direction parabola is built incrementally in registers (one van Leer slope and one
-//    edge value per plane instead of three and two; four -> one Colella-Sekora edge),
-//  * x-neighbour exchange is done with warp shuffles (a warp is one row of the tile), only
-//    y-neighbour exchange goes through shared memory: 5 barriers per plane instead of 6,
-//  * the scalar plane a+LA+1 is staged with cp.async while plane a is being computed and the
-//    velocity / force values of plane a+1 are prefetched into registers,
-//  * no divergent guards: every lane computes, only stores are masked; upwind predicates are
-//    formed once per face and the |u| <= eps averaging arm is skipped warp-uniformly,
-//  * physical-boundary code is compiled out for blocks that do not touch the domain boundary.
-// =========================================================================================
-MXD double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
-MXD double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-
-MXD void cp_async8(double* dst_smem, const double* src, bool pred) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    const int n = pred ? 8 : 0;  // src-size 0: zero-fill, nothing is read
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(n)
-                 : "memory");
-}
-MXD void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-MXD void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-template <int PPM, bool BC, int GY>
-__device__ __forceinline__ void stream_body(const FusedArgs& A, double* smem) {
-    constexpr int GX = 32;
-    constexpr int LA = (PPM == 2) ? 3 : 2;  // stencil radius
-    constexpr int RS = LA + 2;              // ring slots: planes a .. a+LA resident, a+LA+1 in flight
-    constexpr int PW = GX + 2 * LA, PH = GY + 2 * LA;
-    constexpr int NT = GX * GY;
-    constexpr int BX = GX - 2, BY = GY - 2;
-    constexpr int NLD = (PW * PH + NT - 1) / NT;
-
-    double* ring = smem;
-    double* ex = ring + RS * PW * PH;  // y-neighbour exchange arrays (x goes through shuffles)
-    double* X_IPY = ex + 0 * NT;
-    double* X_SY = ex + 1 * NT;
-    double* X_T6X = ex + 2 * NT;
-    double* X_TZ = ex + 3 * NT;
-    double* X_HYX = ex + 4 * NT;
-    double* X_HYZ = ex + 5 * NT;
-    double* X_QY1 = ex + 6 * NT;
-    double* X_QY2 = ex + 7 * NT;
-    double* X_FS = ex + 8 * NT;  // (+ one row of padding behind it)
-
-    const int tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;
-    const int bx = blockIdx.x % A.ntx, by = blockIdx.x / A.ntx;
-    const KGeom& g = A.g;
-    const int x0 = g.vlo[0] + bx * BX, y0 = g.vlo[1] + by * BY;
-    const int thx = min(x0 + BX - 1, g.vhi[0]), thy = min(y0 + BY - 1, g.vhi[1]);
-    const int i = x0 - 1 + tx, j = y0 - 1 + ty;
-    const int k0 = g.vlo[2] + blockIdx.y * A.zc;
-    const int k1 = min(k0 + A.zc, g.vhi[2] + 1);  // exclusive
-    const bool last = (k1 == g.vhi[2] + 1);
-    const int a0 = k0 - 1;
-
-    const bool inG = (i <= thx + 1) && (j <= thy + 1);
-    const bool vxi = inG && tx >= 1 && i <= thx;
-    const bool vyj = inG && ty >= 1 && j <= thy;
-    const bool fx = inG && tx >= 1;
-    const bool fy = inG && ty >= 1;
-    const bool ownx = fx && vyj && (i <= thx || thx == g.vhi[0]);
-    const bool owny = fy && vxi && (j <= thy || thy == g.vhi[1]);
-    const bool ownz = vxi && vyj;
-    const int il = min(i, thx + 1), jl = min(j, thy + 1);  // clamped: every load in bounds
-    const int rc = (ty + LA) * PW + (tx + LA);
-
-    const DFab& st = A.state;
-    const int st_sz = (int)st.sz, f_sz = (int)A.force.sz;
-    const int u_sz = (int)A.umac[0].sz, v_sz = (int)A.umac[1].sz, w_sz = (int)A.umac[2].sz;
-    // per-thread column offsets (plane k adds k * sz; the -lo[2]*sz term is folded in)
-    const int s_co = (int)st.off(il, jl, 0);
-    const int f_co = (int)A.force.off(il, jl, 0);
-    const int u_co = (int)A.umac[0].off(il, jl, 0);
-    const int v_co = (int)A.umac[1].off(il, jl, 0);
-    const int w_co = (int)A.umac[2].off(il, jl, 0);
-    const int ex_co = (int)A.sedge[0].off(il, jl, 0), ey_co = (int)A.sedge[1].off(il, jl, 0),
-              ez_co = (int)A.sedge[2].off(il, jl, 0);
-    const int ex_sz = (int)A.sedge[0].sz, ey_sz = (int)A.sedge[1].sz, ez_sz = (int)A.sedge[2].sz;
-    int fx_co = 0, fy_co = 0, fz_co = 0, fx_sz = 0, fy_sz = 0, fz_sz = 0, eta_co = 0, eta_sz = 0;
-    if (A.mode != 0) {
-        fx_co = (int)A.sflux[0].off(il, jl, 0);
-        fy_co = (int)A.sflux[1].off(il, jl, 0);
-        fz_co = (int)A.sflux[2].off(il, jl, 0);
-        fx_sz = (int)A.sflux[0].sz;
-        fy_sz = (int)A.sflux[1].sz;
-        fz_sz = (int)A.sflux[2].sz;
-        if (A.do_eta) {
-            eta_co = (int)A.eta.off(il, jl, 0);
-            eta_sz = (int)A.eta.sz;
-        }
-    }
-    const double* __restrict__ Up = A.umac[0].p;
-    const double* __restrict__ Vp = A.umac[1].p;
-    const double* __restrict__ Wp = A.umac[2].p;
-
-    // cp.async staging plan of this thread: element e = tid + q*NT of a PW x PH plane
-    int ld_off[NLD];
-    bool ld_do[NLD], ld_in[NLD];
-#pragma unroll
-    for (int q = 0; q < NLD; ++q) {
-        const int e = tid + q * NT;
-        const int px = e % PW, py = e / PW;
-        const int gi = x0 - 1 - LA + px - st.lo[0], gj = y0 - 1 - LA + py - st.lo[1];
-        ld_do[q] = e < PW * PH;
-        ld_in[q] = ld_do[q] && gi >= 0 && gi < st.n[0] && gj >= 0 && gj < st.n[1];
-        ld_off[q] = ld_in[q] ? gj * (int)st.sy + gi : 0;
-    }
-
-    const double c6x = A.c6h[0], c6y = A.c6h[1], c6z = A.c6h[2];
-    const double c4x = A.c4h[0], c4y = A.c4h[1], c4z = A.c4h[2];
-    const double eps = A.eps;
-
-    for (int n = 0; n < A.ncomp; ++n) {
-        const int comp = A.comp[n];
-        const double* __restrict__ sp_ = st.comp(comp);
-        const double* __restrict__ fp_ = A.force.comp(comp);
-        const int bclx = A.bclo[n][0], bchx = A.bchi[n][0];
-        const int bcly = A.bclo[n][1], bchy = A.bchi[n][1];
-        const int bclz = A.bclo[n][2], bchz = A.bchi[n][2];
-        const bool flux1 = (A.mode == 1 && n > 0);
-        const bool flux2 = (A.mode == 2);
-        const bool first_spec = (n == 1);
-
-        auto stage_plane = [&](int k, int slot) {
-            double* dst = ring + slot * PW * PH;
-            const double* src = sp_ + (long)(k - st.lo[2]) * st_sz;
-#pragma unroll
-            for (int q = 0; q < NLD; ++q)
-                if (ld_do[q]) cp_async8(dst + tid + q * NT, src + ld_off[q], ld_in[q]);
-        };
-
-        // ---- prologue ---------------------------------------------------------------
-        __syncthreads();  // previous component is done with shared memory
-#pragma unroll
-        for (int q = 0; q <= LA; ++q) stage_plane(a0 + q, q);
-        cp_async_commit();
-        double zw[2 * LA + 1];
-#pragma unroll
-        for (int m = 0; m < 2 * LA; ++m) zw[m + 1] = sp_[s_co + (a0 - LA + m) * st_sz];
-        zw[0] = 0.0;
-        // incremental z reconstruction state
-        double dz_c = 0.0, ez_lo = 0.0;                 // PPM 1: V(a), E(a-1/2)
-        double ez_l2 = 0.0, ez_l1 = 0.0, ez_h1 = 0.0;   // PPM 2: E(a-3/2), E(a-1/2), E(a+1/2)
-        if (PPM == 1) {
-            const double dm1 = vanleer(zw[1], zw[2], zw[3]);
-            dz_c = vanleer(zw[2], zw[3], zw[4]);
-            ez_lo = vl_edge(zw[2], zw[3], dm1, dz_c);
-        } else if (PPM == 2) {
-            ez_l2 = cs_edge(zw[1], zw[2], zw[3], zw[4]);
-            ez_l1 = cs_edge(zw[2], zw[3], zw[4], zw[5]);
-            ez_h1 = cs_edge(zw[3], zw[4], zw[5], zw[6]);
-        }
-        double w_m1 = 0.0, w_0 = 0.0;
-        double w_p1 = Wp[w_co + a0 * w_sz];
-        // register prefetch of plane a0
-        double um_n = Up[u_co + a0 * u_sz];
-        double up31_n = (tx == 31) ? Up[u_co + a0 * u_sz + 1] : 0.0;
-        double vm_n = Vp[v_co + a0 * v_sz];
-        double vp_n = Vp[v_co + a0 * v_sz + (int)A.umac[1].sy];
-        double w_n = Wp[w_co + (a0 + 1) * w_sz];
-        double f_n = fp_[f_co + a0 * f_sz];
-
-        double ipz_prev = 0.0, shz_prev = 0.0, t6x_prev = 0.0, t6y_prev = 0.0;
-        double slx_p = 0.0, srx_p = 0.0, sly_p = 0.0, sry_p = 0.0, uf_p = 0.0, vf_p = 0.0;
-        double c4x_p = 0.0, c4y_p = 0.0, hzx_prev = 0.0, hzy_prev = 0.0;
-        double t4xy_prev = 0.0, t4yx_prev = 0.0, fs_prev = 0.0;
-        bool slow_p = true;
-        cp_async_wait<0>();
-        __syncthreads();  // planes a0 .. a0+LA are in the ring
-
-        for (int a = a0; a <= k1; ++a) {
-            const int it = a - a0;
-            const double* pa = ring + (it % RS) * PW * PH;
-            // ---- P0: current-plane registers, prefetch of the next plane ----------------
-            const double um = um_n, vm = vm_n, vp = vp_n, f0 = f_n;
-            double up = shfl_dn1(um);
-            if (tx == 31) up = up31_n;
-            w_m1 = w_0;
-            w_0 = w_p1;
-            w_p1 = w_n;
-            if (a + 1 <= k1) stage_plane(a + LA + 1, (it + LA + 1) % RS);
-            cp_async_commit();
-            {
-                const int an = min(a + 1, k1);
-                um_n = Up[u_co + an * u_sz];
-                if (tx == 31) up31_n = Up[u_co + an * u_sz + 1];
-                vm_n = Vp[v_co + an * v_sz];
-                vp_n = Vp[v_co + an * v_sz + (int)A.umac[1].sy];
-                w_n = Wp[w_co + min(a + 2, k1 + 1) * w_sz];
-                f_n = fp_[f_co + an * f_sz];
-            }
-            // velocity predicates of this plane's faces
-            const bool px_pos = um > 0.0, px_nz0 = fabs(um) > 0.0, px_nz = fabs(um) > eps;
-            const bool py_pos = vm > 0.0, py_nz0 = fabs(vm) > 0.0, py_nz = fabs(vm) > eps;
-            const bool pz_pos = w_0 > 0.0, pz_nz0 = fabs(w_0) > 0.0, pz_nz = fabs(w_0) > eps;
-            const bool slow_c = __any_sync(
-                0xffffffffu, !(px_nz0 && px_nz && py_nz0 && py_nz && pz_nz0 && pz_nz));
-            const bool slow = slow_c || slow_p;
-
-            // ---- P1: x / y reconstruction of plane a ------------------------------------
-            const double s0 = pa[rc];
-            double ipx, imx, ipy, imy;
-            {
-                double S[7];
-                S[0] = S[6] = 0.0;
-#pragma unroll
-                for (int q = -LA; q <= LA; ++q) S[q + 3] = pa[rc + q];
-                reconstruct<PPM, BC, 0>(A, S, i, bclx, bchx, um, up, ipx, imx);
-#pragma unroll
-                for (int q = -LA; q <= LA; ++q) S[q + 3] = pa[rc + q * PW];
-                reconstruct<PPM, BC, 1>(A, S, j, bcly, bchy, vm, vp, ipy, imy);
-            }
-            X_IPY[tid] = ipy;
-            cp_async_wait<1>();  // this thread's share of plane a+LA has landed
-            __syncthreads();     // S2: publishes IPY and ring plane a+LA
-
-            // ---- P2: z reconstruction, 1-D states, first Riemann solve -------------------
-#pragma unroll
-            for (int m = 0; m < 2 * LA; ++m) zw[m] = zw[m + 1];
-            zw[2 * LA] = ring[((it + LA) % RS) * PW * PH + rc];
-            double ipz, imz;
-            {
-                double S[7];
-                S[0] = S[6] = 0.0;
-#pragma unroll
-                for (int q = -LA; q <= LA; ++q) S[q + 3] = zw[q + LA];
-                if (PPM == 0) {
-                    reconstruct<PPM, BC, 2>(A, S, a, bclz, bchz, w_0, w_p1, ipz, imz);
-                } else {
-                    const bool lobc = BC && (bclz == BC_EXT_DIR || bclz == BC_HOEXTRAP);
-                    const bool hibc = BC && (bchz == BC_EXT_DIR || bchz == BC_HOEXTRAP);
-                    double sm, sp;
-                    if (PPM == 1) {
-                        const double dz_n = vanleer(S[3], S[4], S[5]);
-                        const double ez_hi = vl_edge(S[3], S[4], dz_c, dz_n);
-                        ppm1_finish<BC>(S, a, g.dlo[2], g.dhi[2], lobc, hibc, ez_lo, ez_hi, sm, sp);
-                        dz_c = dz_n;
-                        ez_lo = ez_hi;
-                    } else {
-                        const double ez_h2 = cs_edge(S[3], S[4], S[5], S[6]);
-                        ppm2_finish<BC>(S, a, g.dlo[2], g.dhi[2], lobc, hibc, false, ez_l2, ez_l1,
-                                        ez_h1, ez_h2, sm, sp);
-                        ez_l2 = ez_l1;
-                        ez_l1 = ez_h1;
-                        ez_h1 = ez_h2;
-                    }
-                    const double s6 = 6.0 * s0 - 3.0 * (sm + sp);
-                    const double sig_p = over_h<2>(A, fabs(w_p1) * A.dt);
-                    const double sig_m = over_h<2>(A, fabs(w_0) * A.dt);
-                    ipz = ppm_Ip(sm, sp, s0, s6, w_p1, sig_p, eps);
-                    imz = ppm_Im(sm, sp, s0, s6, w_0, sig_m, eps);
-                }
-            }
-            double slx, srx, sly, sry, slz, srz;
-            face_states<PPM, 0>(A, um, pa[rc - 1], s0, shfl_up1(ipx), ipx, imx, slx, srx);
-            if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, slx, srx);
-            const double shx = upw(px_pos, px_nz0, slow, slx, srx);  // QUIRK: |u| > 0.0 (:746)
-            face_states<PPM, 1>(A, vm, pa[rc - PW], s0, X_IPY[tid - GX], ipy, imy, sly, sry);
-            if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, sly, sry);
-            const double shy = upw(py_pos, py_nz0, slow, sly, sry);
-            face_states<PPM, 2>(A, w_0, zw[LA - 1], s0, ipz_prev, ipz, imz, slz, srz);
-            if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, slz, srz);
-            const double shz = upw(pz_pos, pz_nz0, slow, slz, srz);
-            X_SY[tid] = shy;
-            __syncthreads();  // S3
-
-            // ---- P3: transverse differences (dt/6 form) ---------------------------------
-            const double usx = up + um, usy = vp + vm;
-            const double t6x = (c6x * usx) * (shfl_dn1(shx) - shx);
-            const double t6y = (c6y * usy) * (X_SY[tid + GX] - shy);
-            const double wsum_p = w_0 + w_m1;  // faces a and a-1: cell a-1
-            const double tz = (c6z * wsum_p) * (shz - shz_prev);
-            X_T6X[tid] = t6x;
-            X_TZ[tid] = tz;
-            __syncthreads();  // S4
-
-            // ---- P4: corner-coupled states ----------------------------------------------
-            const bool qx_pos = uf_p > 0.0, qx_nz = fabs(uf_p) > eps;
-            const bool qy_pos = vf_p > 0.0, qy_nz = fabs(vf_p) > eps;
-            double hxy, hyx, hzx, hzy, hxz, hyz;
-            {
-                double l = slx - shfl_up1(t6y), r = srx - t6y;
-                if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, l, r);
-                hxy = upw(px_pos, px_nz, slow, l, r);
-                l = sly - X_T6X[tid - GX];
-                r = sry - t6x;
-                if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, l, r);
-                hyx = upw(py_pos, py_nz, slow, l, r);
-                l = slz - t6x_prev;
-                r = srz - t6x;
-                if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, l, r);
-                hzx = upw(pz_pos, pz_nz, slow, l, r);
-                l = slz - t6y_prev;
-                r = srz - t6y;
-                if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, l, r);
-                hzy = upw(pz_pos, pz_nz, slow, l, r);
-                l = slx_p - shfl_up1(tz);
-                r = srx_p - tz;
-                if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, l, r);
-                hxz = upw(qx_pos, qx_nz, slow, l, r);
-                l = sly_p - X_TZ[tid - GX];
-                r = sry_p - tz;
-                if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, l, r);
-                hyz = upw(qy_pos, qy_nz, slow, l, r);
-            }
-            X_HYX[tid] = hyx;
-            X_HYZ[tid] = hyz;
-            __syncthreads();  // S5
-
-            // ---- P5: transverse differences (dt/4 form) ---------------------------------
-            const double c4xu = c4x * usx, c4yu = c4y * usy, c4zw = c4z * wsum_p;
-            const double t4xy = c4xu * (shfl_dn1(hxy) - hxy);
-            const double t4yx = c4yu * (X_HYX[tid + GX] - hyx);
-            const double t4yz = c4y_p * (X_HYZ[tid + GX] - hyz);
-            const double t4zy = c4zw * (hzy - hzy_prev);
-            const double t4xz = c4x_p * (shfl_dn1(hxz) - hxz);
-            const double t4zx = c4zw * (hzx - hzx_prev);
-            const double fs_cur = A.dt2 * f0;
-            X_QY1[tid] = t4xz;
-            X_QY2[tid] = t4zx;
-            X_FS[tid] = fs_prev;
-            __syncthreads();  // S6
-
-            // ---- P6: final edge states (+ fluxes) ---------------------------------------
-            {
-                const int p = a - 1;
-                // x faces of plane p
-                {
-                    const double el = ((slx_p - shfl_up1(t4yz)) - shfl_up1(t4zy)) + shfl_up1(fs_prev);
-                    const double er = ((srx_p - t4yz) - t4zy) + fs_prev;
-                    double val = upw(qx_pos, qx_nz, slow, el, er);
-                    if (BC)
-                        val = bc_final(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, el, er, val);
-                    if (ownx && a >= k0 + 1) {
-                        const DFab& E = A.sedge[0];
-                        const int eo = ex_co + p * ex_sz;
-                        E.comp(comp)[eo] = val;
-                        if (flux1) {
-                            const DFab& F = A.sflux[0];
-                            const int fo = fx_co + p * fx_sz;
-                            const double ser = E.comp(A.f.rho)[eo];
-                            const double r0e =
-                                A.f.spherical ? 0.5 * A.r0o[0].p[A.r0o[0].off(i, j, p)] +
-                                                    0.5 * A.r0n[0].p[A.r0n[0].off(i, j, p)]
-                                              : rho0_edge_planar(A.f, false, p);
-                            const double fl = rhoX_flux(A.f.spt, uf_p, r0e, ser, val);
-                            F.comp(comp)[fo] = fl;
-                            F.comp(A.f.rho)[fo] = (first_spec ? 0.0 : F.comp(A.f.rho)[fo]) + fl;
-                        } else if (flux2) {
-                            const DFab& F = A.sflux[0];
-                            const double ser = needs_sedge_rho_for_rhoh(A.f) ? E.comp(A.f.rho)[eo] : 0.0;
-                            double fl;
-                            if (rhoh_flux_planar(A.f, false, p, uf_p, ser, val, &fl))
-                                F.comp(comp)[fx_co + p * fx_sz] = fl;
-                        }
-                    }
-                }
-                // y faces of plane p
-                {
-                    const double el = ((sly_p - X_QY1[tid - GX]) - X_QY2[tid - GX]) + X_FS[tid - GX];
-                    const double er = ((sry_p - t4xz) - t4zx) + fs_prev;
-                    double val = upw(qy_pos, qy_nz, slow, el, er);
-                    if (BC)
-                        val = bc_final(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, el, er, val);
-                    if (owny && a >= k0 + 1) {
-                        const DFab& E = A.sedge[1];
-                        const int eo = ey_co + p * ey_sz;
-                        E.comp(comp)[eo] = val;
-                        if (flux1) {
-                            const DFab& F = A.sflux[1];
-                            const int fo = fy_co + p * fy_sz;
-                            const double ser = E.comp(A.f.rho)[eo];
-                            const double r0e =
-                                A.f.spherical ? 0.5 * A.r0o[1].p[A.r0o[1].off(i, j, p)] +
-                                                    0.5 * A.r0n[1].p[A.r0n[1].off(i, j, p)]
-                                              : rho0_edge_planar(A.f, false, p);
-                            const double fl = rhoX_flux(A.f.spt, vf_p, r0e, ser, val);
-                            F.comp(comp)[fo] = fl;
-                            F.comp(A.f.rho)[fo] = (first_spec ? 0.0 : F.comp(A.f.rho)[fo]) + fl;
-                        } else if (flux2) {
-                            const DFab& F = A.sflux[1];
-                            const double ser = needs_sedge_rho_for_rhoh(A.f) ? E.comp(A.f.rho)[eo] : 0.0;
-                            double fl;
-                            if (rhoh_flux_planar(A.f, false, p, vf_p, ser, val, &fl))
-                                F.comp(comp)[fy_co + p * fy_sz] = fl;
-                        }
-                    }
-                }
-                // z face a
-                {
-                    const double el = ((slz - t4xy_prev) - t4yx_prev) + fs_prev;
-                    const double er = ((srz - t4xy) - t4yx) + fs_cur;
-                    double val = upw(pz_pos, pz_nz, slow, el, er);
-                    if (BC)
-                        val = bc_final(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, el, er, val);
-                    if (ownz && a >= k0 && (a <= k1 - 1 || last)) {
-                        const DFab& E = A.sedge[2];
-                        const int eo = ez_co + a * ez_sz;
-                        E.comp(comp)[eo] = val;
-                        if (flux1) {
-                            const DFab& F = A.sflux[2];
-                            const int fo = fz_co + a * fz_sz;
-                            const double ser = E.comp(A.f.rho)[eo];
-                            const double r0e = A.f.spherical
-                                                   ? 0.5 * A.r0o[2].p[A.r0o[2].off(i, j, a)] +
-                                                         0.5 * A.r0n[2].p[A.r0n[2].off(i, j, a)]
-                                                   : rho0_edge_planar(A.f, true, a);
-                            const double fl = rhoX_flux(A.f.spt, w_0, r0e, ser, val);
-                            F.comp(comp)[fo] = fl;
-                            F.comp(A.f.rho)[fo] = (first_spec ? 0.0 : F.comp(A.f.rho)[fo]) + fl;
-                            if (A.do_eta) {
-                                // MaestroMakeFlux.cpp:288-301
-                                double* ep = A.eta.p + (eta_co + a * eta_sz);
-                                double ev = *ep;
-                                if (comp >= A.f.first_spec && comp <= A.f.first_spec + A.f.num_spec - 1)
-                                    ev += fl;
-                                if (comp == A.f.first_spec + A.f.num_spec - 1)
-                                    ev -= A.f.w0[a * A.f.st_w0] *
-                                          A.f.rho0_pred_edge[a * A.f.st_rho0_pred_edge];
-                                *ep = ev;
-                            }
-                        } else if (flux2) {
-                            const DFab& F = A.sflux[2];
-                            const double ser = needs_sedge_rho_for_rhoh(A.f) ? E.comp(A.f.rho)[eo] : 0.0;
-                            double fl;
-                            if (rhoh_flux_planar(A.f, true, a, w_0, ser, val, &fl))
-                                F.comp(comp)[fz_co + a * fz_sz] = fl;
-                        }
-                    }
-                }
-            }
-
-            // ---- rotate the per-thread z history ------------------------------------------
-            ipz_prev = ipz;
-            shz_prev = shz;
-            t6x_prev = t6x;
-            t6y_prev = t6y;
-            slx_p = slx;
-            srx_p = srx;
-            sly_p = sly;
-            sry_p = sry;
-            uf_p = um;
-            vf_p = vm;
-            c4x_p = c4xu;
-            c4y_p = c4yu;
-            hzx_prev = hzx;
-            hzy_prev = hzy;
-            t4xy_prev = t4xy;
-            t4yx_prev = t4yx;
-            fs_prev = fs_cur;
-            slow_p = slow_c;
-        }
-        cp_async_wait<0>();
-    }
-}
-
-template <int PPM, int GY>
-__global__ void __launch_bounds__(32 * GY, (GY >= 16) ? 1 : 2)
-    k_stream(const __grid_constant__ FusedArgs A) {
-    extern __shared__ double sm[];
-    // physical-boundary code only in blocks whose (grown) tile reaches a domain face that has
-    // a non-interior BC; everything else runs the BC-free instantiation
-    constexpr int BX = 30, BY = GY - 2;
-    const KGeom& g = A.g;
-    const int bx = blockIdx.x % A.ntx, by = blockIdx.x / A.ntx;
-    const int x0 = g.vlo[0] + bx * BX, y0 = g.vlo[1] + by * BY;
-    const int k0 = g.vlo[2] + blockIdx.y * A.zc;
-    bool bc = false;
-    if (A.bcdir[0]) bc |= (x0 - 1 <= g.dlo[0] + 2) || (x0 + BX >= g.dhi[0] - 2);
-    if (A.bcdir[1]) bc |= (y0 - 1 <= g.dlo[1] + 2) || (y0 + BY >= g.dhi[1] - 2);
-    if (A.bcdir[2]) bc |= (k0 - 1 <= g.dlo[2] + 2) || (k0 + A.zc >= g.dhi[2] - 2);
-    if (bc)
-        stream_body<PPM, true, GY>(A, sm);
-    else
-        stream_body<PPM, false, GY>(A, sm);
-}
-
-template <int PPM, int GY>
-int launch_stream(const FusedArgs& A, cudaStream_t stream) {
-    constexpr int LA = (PPM == 2) ? 3 : 2;
-    constexpr int RS = LA + 2, GX = 32;
-    constexpr int PW = GX + 2 * LA, PH = GY + 2 * LA;
-    const size_t smem = sizeof(double) * (size_t)(RS * PW * PH + 9 * GX * GY + GX);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_stream<PPM, GY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
-            return -1;
-        attr_set = true;
-    }
-    const int nz = A.g.vhi[2] - A.g.vlo[2] + 1;
-    dim3 grid(A.ntx * A.nty, (nz + A.zc - 1) / A.zc);
-    k_stream<PPM, GY><<<grid, GX * GY, smem, stream>>>(A);
-    mx_count_launch();
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
+#include "mx_stream.cuh"
 
 template <int PPM, bool BC, int GX, int GY>
 int launch(const FusedArgs& A, cudaStream_t stream) {
@@ -1037,19 +536,12 @@ int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
     const char* kv = getenv("MXADV_KERNEL");
     const bool v1 = (kv && kv[0] == 'v' && kv[1] == '1') || !stream_ok(A);
     if (!v1) {
-        const char* gy = getenv("MXADV_GY");
-        const int GY = gy ? atoi(gy) : 16;
         A.ntx = (nx + 29) / 30;
-        if (GY == 8) {
-            A.nty = (ny + 5) / 6;
-            if (ppm_type == 0) return launch_stream<0, 8>(A, stream);
-            if (ppm_type == 1) return launch_stream<1, 8>(A, stream);
-            return launch_stream<2, 8>(A, stream);
-        }
         A.nty = (ny + 13) / 14;
-        if (ppm_type == 0) return launch_stream<0, 16>(A, stream);
-        if (ppm_type == 1) return launch_stream<1, 16>(A, stream);
-        return launch_stream<2, 16>(A, stream);
+        if (A.zc > ST_MAXZC) A.zc = ST_MAXZC;
+        if (ppm_type == 0) return launch_stream_mode<0>(A, stream);
+        if (ppm_type == 1) return launch_stream_mode<1>(A, stream);
+        return launch_stream_mode<2>(A, stream);
     }
     A.ntx = (nx + (FGX - 2) - 1) / (FGX - 2);
     A.nty = (ny + (FGY - 2) - 1) / (FGY - 2);
