@@ -14,7 +14,8 @@ for l in open(sass):
         if m: off2line[int(m.group(1), 16)] = cur
 lines = open(srccsv).read().splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rd = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+end = next((i for i, l in enumerate(lines) if i > start and l.startswith('"Kernel Name"')), len(lines))
+rd = list(csv.DictReader(io.StringIO("\n".join(lines[start:end]))))
 def addr(r):
     a = r['Address']; return int(a, 16) if a.startswith('0x') else int(a)
 base = addr(rd[0])

@@ -28,7 +28,8 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-i
                      capture_output=True, text=True).stdout
 lines = src.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rd = csv.DictReader(io.StringIO("\n".join(lines[start:])))
+end = next((i for i, l in enumerate(lines) if i > start and l.startswith('"Kernel Name"')), len(lines))
+rd = csv.DictReader(io.StringIO("\n".join(lines[start:end])))
 stall = collections.Counter(); ops = collections.Counter(); tot = 0; execd = 0
 for row in rd:
     try:
