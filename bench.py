@@ -177,19 +177,6 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def rank_grid(world):
-    """bricks per direction (minimum surface): 1,2,4,8 -> (1,1,1),(2,1,1),(2,2,1),(2,2,2)."""
-    p = [1, 1, 1]
-    d = 0
-    w = world
-    while w > 1:
-        assert w % 2 == 0, "world size must be a power of two"
-        p[d % 3] *= 2
-        w //= 2
-        d += 1
-    return tuple(p)
-
-
 def run_mxadv(a):
     import torch
     import torch.distributed as dist
@@ -212,8 +199,10 @@ def run_mxadv(a):
     calls = mxlib.calls()
     ng = 4 if a.ppm == 2 else 3
     n = a.n
+    from maestroex_b200.decomp import Brick, DevicePacker, HaloExchanger, rank_grid
     pg = rank_grid(world)
-    coord = (rank % pg[0], (rank // pg[0]) % pg[1], rank // (pg[0] * pg[1]))
+    brick = Brick(rank, pg)
+    coord = brick.coord
     prob = make_device_problem(n=(n, n, n), nspec=a.nspec, ng=ng, bc_kind=a.bc,
                                seed=20240807 + rank, device=str(dev),
                                dom_n=tuple(n * pg[d] for d in range(3)),
@@ -226,8 +215,8 @@ def run_mxadv(a):
 
     halo = None
     if world > 1 and not a.no_halo:
-        from maestroex_b200.decomp import HaloExchanger
-        halo = HaloExchanger(calls, prob, pg, coord, rank, world, ng)
+        halo = HaloExchanger(prob.geom, prob.state, prob.bc, brick, ng,
+                             DevicePacker(calls, dev))
 
     def step(ev=None):
         if halo is not None:
