@@ -7,7 +7,7 @@ MakeRhoXFlux: Source/MaestroDensityAdvance.cpp:115,128,182) followed by the ENTH
 (MakeEdgeScal on (rho h)' + MakeRhoHFlux: Source/MaestroEnthalpyAdvance.cpp:141,229), i.e.
 zones x (nspec + 2) zone-species updates, through the C ABI of libmxadv.so.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--nspec 13] [--ppm 1]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--nspec 13] [--ppm 1]
   python bench.py --impl reference ...     # the reference's own CPU code (oracle/_ref)
 
 N > 1: launched by torchrun, one rank per GPU; every rank owns one n^3 brick of a
@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mxadv", choices=["mxadv", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="brick edge (zones) per GPU")
+    ap.add_argument("--size", dest="n", type=int, default=512, help="brick edge (zones) per GPU")
     ap.add_argument("--nspec", type=int, default=13)
     ap.add_argument("--ppm", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--bc", default="reacting_bubble")

@@ -42,3 +42,16 @@ def reference(dim: int = 3):
         if not os.path.exists(path):
             return None
     return Calls(C.CDLL(path), "ref_", with_stream=False)
+
+
+@lru_cache(maxsize=None)
+def overlay(dim: int = 3):
+    """The PRODUCT's C++ overlay (maestroex_b200/overlay: `Maestro::` members on libmxadv.so)
+    behind the same driver as ``reference`` (exports ``ovl_*``); ``None`` if not built."""
+    path = os.path.join(HERE, "_ref", f"libmxadv_overlay{dim}d.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference/Source"):
+            build(ref=True)
+        if not os.path.exists(path):
+            return None
+    return Calls(C.CDLL(path), "ovl_", with_stream=False)

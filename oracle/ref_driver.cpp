@@ -9,6 +9,15 @@
 
 #include "../include/mxadv.h"
 
+// The same driver also fronts the PRODUCT's overlay (maestroex_b200/overlay/*.cpp, the
+// `Maestro::` members implemented on libmxadv.so) when compiled with -DDRV_OVERLAY: exports
+// are then named ovl_* and tests/test_gpu_overlay.py runs reference and overlay side by side.
+#ifdef DRV_OVERLAY
+#define DRV(name) ovl_##name
+#else
+#define DRV(name) ref_##name
+#endif
+
 using namespace amrex;
 
 // ---- definitions of the globals the shim header declares -------------------------------
@@ -103,9 +112,9 @@ void set_flux_globals(const MxFluxParams* p) {
 
 extern "C" {
 
-int ref_dim(void) { return DIM; }
+int DRV(dim)(void) { return DIM; }
 
-int ref_num_threads(void) {
+int DRV(num_threads)(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
 #else
@@ -113,7 +122,7 @@ int ref_num_threads(void) {
 #endif
 }
 
-void ref_set_num_threads(int n) {
+void DRV(set_num_threads)(int n) {
 #ifdef _OPENMP
     omp_set_num_threads(n);
 #else
@@ -122,7 +131,7 @@ void ref_set_num_threads(int n) {
 }
 
 // Maestro::MakeEdgeScal, Source/MaestroMakeEdgeScalars.cpp:6
-int ref_make_edge_scal(const MxGeom* g, const MxFab* state, const MxFab* sedge,
+int DRV(make_edge_scal)(const MxGeom* g, const MxFab* state, const MxFab* sedge,
                        const MxFab* umac, const MxFab* force, const MxEdgeParams* p) {
     Maestro m;
     setup(m, g);
@@ -153,7 +162,7 @@ int ref_make_edge_scal(const MxGeom* g, const MxFab* state, const MxFab* sedge,
 }
 
 // Maestro::MakeRhoXFlux, Source/MaestroMakeFlux.cpp:18
-int ref_make_rhoX_flux(const MxGeom* g, const MxFab* sflux, const MxFab* etarhoflux,
+int DRV(make_rhoX_flux)(const MxGeom* g, const MxFab* sflux, const MxFab* etarhoflux,
                        const MxFab* sedge, const MxFab* umac, const MxBase* rho0_old,
                        const MxBase* rho0_edge_old, const MxFab* r0mac_old,
                        const MxBase* rho0_new, const MxBase* rho0_edge_new,
@@ -189,7 +198,7 @@ int ref_make_rhoX_flux(const MxGeom* g, const MxFab* sflux, const MxFab* etarhof
 }
 
 // Maestro::MakeRhoHFlux, Source/MaestroMakeFlux.cpp:467
-int ref_make_rhoh_flux(const MxGeom* g, const MxFab* sflux, const MxFab* sedge,
+int DRV(make_rhoh_flux)(const MxGeom* g, const MxFab* sflux, const MxFab* sedge,
                        const MxFab* umac, const MxBase* rho0_old,
                        const MxBase* rho0_edge_old, const MxFab* r0mac_old,
                        const MxBase* rho0_new, const MxBase* rho0_edge_new,
@@ -233,7 +242,7 @@ int ref_make_rhoh_flux(const MxGeom* g, const MxFab* sflux, const MxFab* sedge,
 }
 
 // Maestro::CelltoEdge, Source/MaestroCelltoEdge.cpp:5 — one level, one chunk [r_lo, r_hi]
-int ref_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi) {
+int DRV(cell_to_edge)(const double* cell, double* edge, int nr, int r_lo, int r_hi) {
     Maestro m;
     maestro::spherical = false;
     // base_geom tables: BaseStateArray views over local storage
