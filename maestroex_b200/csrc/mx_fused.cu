@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(GX* GY, 1) k_fused(const __grid_constant__ Fus
 
 
 #include "mx_stream.cuh"
+#include "mx_stream4.cuh"
 
 template <int PPM, bool BC, int GX, int GY>
 int launch(const FusedArgs& A, cudaStream_t stream) {
@@ -539,6 +540,12 @@ int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
         A.ntx = (nx + 29) / 30;
         A.nty = (ny + 13) / 14;
         if (A.zc > ST_MAXZC) A.zc = ST_MAXZC;
+        const bool v3 = kv && kv[0] == 'v' && kv[1] == '3';
+        if (!v3) {
+            if (ppm_type == 0) return launch_stream4_mode<0>(A, stream);
+            if (ppm_type == 1) return launch_stream4_mode<1>(A, stream);
+            return launch_stream4_mode<2>(A, stream);
+        }
         if (ppm_type == 0) return launch_stream_mode<0>(A, stream);
         if (ppm_type == 1) return launch_stream_mode<1>(A, stream);
         return launch_stream_mode<2>(A, stream);
