@@ -224,6 +224,45 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
 int mx_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi,
                     void* stream);
 
+/* ---- Maestro::Makew0 ---------------------------------------------------------------------
+ * Runtime parameters and base-state geometry read by Maestro::Makew0Planar / Makew0Sphr
+ * (Source/MaestroMakew0.cpp:60-272,537-740; base_geom = Source/BaseStateGeometry.H;
+ * maestro.* parameters Source/param/_cpp_parameters:309,331,385,391). */
+typedef struct MxW0Params {
+    int nr_fine;                   /* base_geom.nr_fine */
+    int base_cutoff_density_coord; /* base_geom.base_cutoff_density_coord(0) */
+    int is_predictor;              /* planar only (:151-163) */
+    int add_pb;                    /* planar closed-box pressure correction (:175-184) */
+    double dr;                     /* base_geom.dr(0) */
+    double dt;                     /* the Maestro member `dt` (planar delta_chi_w0, :103) */
+    double dt_in, dtold_in;        /* the dt_in / dtold_in arguments */
+    double grav_const, dpdt_factor, base_cutoff_density;
+} MxW0Params;
+
+/* Replaces Maestro::Makew0 -> Makew0Planar (Source/MaestroMakew0.cpp:5-58,60-272) for ONE
+ * radial level (max_radial_level == 0, one disjoint chunk [0, nr_fine-1]; multilevel
+ * restriction / offset :185-213 is the caller's).  Cell-centred inputs have
+ * nr_fine entries, w0_old and w0 nr_fine+1.  Writes the Maestro member w0 (all nr_fine+1
+ * edges), w0_force (nr_fine cells) and, if add_pb, *p0bdot (HOST pointer, may be NULL; the
+ * caller sets p0b = p0bdot * dt, :178-180).  Arrays may be host or device resident. */
+int mx_make_w0_planar(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                      const double* p0_old, const double* p0_new, const double* gamma1bar_old,
+                      const double* gamma1bar_new, const double* p0_minus_peosbar,
+                      const double* etarho_cc, double* w0, double* w0_force, double* p0bdot,
+                      void* stream);
+
+/* Replaces Maestro::Makew0 -> Makew0Sphr (Source/MaestroMakew0.cpp:537-740) including the
+ * calls it makes: MakeGravEdge, spherical branch (Source/MaestroMakeGrav.cpp:303-322) and
+ * Tridiag (:942-969).  r_cc_loc (nr_fine) and r_edge_loc (nr_fine+1) are level 0 of
+ * base_geom.r_cc_loc / r_edge_loc; etarho_ec has nr_fine+1 entries.  use_exact_base_state
+ * (Makew0SphrIrreg) is not supported. */
+int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                    const double* rho0_old, const double* rho0_new, const double* p0_old,
+                    const double* p0_new, const double* gamma1bar_old,
+                    const double* gamma1bar_new, const double* p0_minus_peosbar,
+                    const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
+                    const double* r_edge_loc, double* w0, double* w0_force, void* stream);
+
 /* ---- ghost-cell exchange between the bricks of one box (multi-GPU) -----------------------
  * Packs / unpacks the `ng`-deep face slab `side` (0 = lo, 1 = hi) of direction `dir` of
  * components [comp0, comp0+ncomp) of a fab into / from a contiguous device buffer, i.e. the

@@ -74,6 +74,22 @@ class MxFluxParams(C.Structure):
     ]
 
 
+class MxW0Params(C.Structure):
+    _fields_ = [
+        ("nr_fine", C.c_int),
+        ("base_cutoff_density_coord", C.c_int),
+        ("is_predictor", C.c_int),
+        ("add_pb", C.c_int),
+        ("dr", C.c_double),
+        ("dt", C.c_double),
+        ("dt_in", C.c_double),
+        ("dtold_in", C.c_double),
+        ("grav_const", C.c_double),
+        ("dpdt_factor", C.c_double),
+        ("base_cutoff_density", C.c_double),
+    ]
+
+
 # AMReX BCType codes (external/amrex/Src/Base/AMReX_BC_TYPES.H:68-76)
 BC_REFLECT_ODD, BC_INT_DIR, BC_REFLECT_EVEN, BC_FOEXTRAP, BC_EXT_DIR, BC_HOEXTRAP = -1, 0, 1, 2, 3, 4
 
@@ -230,6 +246,29 @@ class FluxParams:
         p = MxFluxParams()
         for name, _ in MxFluxParams._fields_:
             setattr(p, name, int(getattr(self, name)))
+        return p
+
+
+@dataclass
+class W0Params:
+    """Arguments / parameters of Maestro::Makew0 (Source/MaestroMakew0.cpp:5-14,60-69)."""
+    nr_fine: int
+    base_cutoff_density_coord: int
+    dr: float
+    dt: float
+    dt_in: float
+    dtold_in: float
+    is_predictor: int = 1
+    add_pb: int = 0
+    grav_const: float = -1.5e10
+    dpdt_factor: float = 0.0
+    base_cutoff_density: float = -1.0
+
+    def c(self) -> MxW0Params:
+        p = MxW0Params()
+        for name, typ in MxW0Params._fields_:
+            v = getattr(self, name)
+            setattr(p, name, int(v) if typ is C.c_int else float(v))
         return p
 
 

@@ -6,7 +6,7 @@
 same argument lists without the stream (see oracle/backends.py).
 Argument order and meaning follow the reference member functions
 (Source/MaestroMakeEdgeScalars.cpp:6, Source/MaestroMakeFlux.cpp:18,467,
-Source/MaestroCelltoEdge.cpp:5).
+Source/MaestroCelltoEdge.cpp:5, Source/MaestroMakew0.cpp:5).
 """
 from __future__ import annotations
 
@@ -95,3 +95,33 @@ class Calls:
                                       C.c_int(nr), C.c_int(r_lo), C.c_int(r_hi),
                                       *self._tail(stream))
         self._check(rc, "cell_to_edge")
+
+    # -- Maestro::Makew0 --------------------------------------------------------------
+    @staticmethod
+    def _vp(a):
+        from .abi import _ptr_of
+        return C.c_void_p(_ptr_of(a)) if a is not None else None
+
+    def make_w0_planar(self, par, w0_old, Sbar, p0_old, p0_new, gamma1bar_old, gamma1bar_new,
+                       p0_minus_peosbar, etarho_cc, w0, w0_force, stream: int = 0):
+        """Returns p0bdot (0.0 unless par.add_pb)."""
+        p = par.c()
+        pb = C.c_double(0.0)
+        v = self._vp
+        rc = self._fn("make_w0_planar")(
+            C.byref(p), v(w0_old), v(Sbar), v(p0_old), v(p0_new), v(gamma1bar_old),
+            v(gamma1bar_new), v(p0_minus_peosbar), v(etarho_cc), v(w0), v(w0_force),
+            C.byref(pb), *self._tail(stream))
+        self._check(rc, "make_w0_planar")
+        return pb.value
+
+    def make_w0_sphr(self, par, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new,
+                     gamma1bar_old, gamma1bar_new, p0_minus_peosbar, etarho_cc, etarho_ec,
+                     r_cc_loc, r_edge_loc, w0, w0_force, stream: int = 0):
+        p = par.c()
+        v = self._vp
+        rc = self._fn("make_w0_sphr")(
+            C.byref(p), v(w0_old), v(Sbar), v(rho0_old), v(rho0_new), v(p0_old), v(p0_new),
+            v(gamma1bar_old), v(gamma1bar_new), v(p0_minus_peosbar), v(etarho_cc),
+            v(etarho_ec), v(r_cc_loc), v(r_edge_loc), v(w0), v(w0_force), *self._tail(stream))
+        self._check(rc, "make_w0_sphr")

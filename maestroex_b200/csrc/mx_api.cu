@@ -11,6 +11,7 @@
 
 #include "mx_common.h"
 #include "mx_flux.h"
+#include "mx_w0.h"
 #include "mx_fused.h"
 #include "mx_staged.h"
 
@@ -663,6 +664,117 @@ int mx_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi
                                 S.stream()));
     }
     if (hc || he) CUDA_OK(cudaStreamSynchronize(S.stream()));
+    return MX_OK;
+}
+
+// ---- Maestro::Makew0 ------------------------------------------------------------------
+namespace {
+// device view of a 1-D array of n doubles: host arrays are mirrored (uploaded when `in`)
+int w0_arr(Session& S, const double* src, size_t n, bool in, const double** dev, bool* host) {
+    *host = false;
+    if (src == nullptr) return fail(MX_ERR_INVALID, "null base-state array");
+    if (is_device_ptr(src)) {
+        *dev = src;
+        return MX_OK;
+    }
+    void* p = nullptr;
+    CUDA_OK(S.alloc(&p, sizeof(double) * n));
+    if (in) CUDA_OK(cudaMemcpyAsync(p, src, sizeof(double) * n, cudaMemcpyHostToDevice, S.stream()));
+    *dev = static_cast<const double*>(p);
+    *host = true;
+    return MX_OK;
+}
+int check_w0_params(const MxW0Params* p) {
+    if (p == nullptr) return fail(MX_ERR_INVALID, "null MxW0Params");
+    if (p->nr_fine < 2) return fail(MX_ERR_INVALID, "nr_fine = %d", p->nr_fine);
+    if (!(p->dr > 0.0)) return fail(MX_ERR_INVALID, "dr must be positive");
+    if (p->base_cutoff_density_coord < 0)
+        return fail(MX_ERR_INVALID, "base_cutoff_density_coord = %d", p->base_cutoff_density_coord);
+    return MX_OK;
+}
+}  // namespace
+
+int mx_make_w0_planar(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                      const double* p0_old, const double* p0_new, const double* gamma1bar_old,
+                      const double* gamma1bar_new, const double* p0_minus_peosbar,
+                      const double* etarho_cc, double* w0, double* w0_force, double* p0bdot,
+                      void* stream) {
+    MX_TRY(check_w0_params(par));
+    MX_TRY(require_device());
+    Session S(stream);
+    const size_t nr = (size_t)par->nr_fine;
+    const double *d_w0o, *d_S, *d_p0o, *d_p0n, *d_g1o, *d_g1n, *d_pmp, *d_eta, *d_w0, *d_f;
+    bool h, h_w0, h_f;
+    MX_TRY(w0_arr(S, w0_old, nr + 1, true, &d_w0o, &h));
+    MX_TRY(w0_arr(S, Sbar, nr, true, &d_S, &h));
+    MX_TRY(w0_arr(S, p0_old, nr, true, &d_p0o, &h));
+    MX_TRY(w0_arr(S, p0_new, nr, true, &d_p0n, &h));
+    MX_TRY(w0_arr(S, gamma1bar_old, nr, true, &d_g1o, &h));
+    MX_TRY(w0_arr(S, gamma1bar_new, nr, true, &d_g1n, &h));
+    MX_TRY(w0_arr(S, p0_minus_peosbar, nr, true, &d_pmp, &h));
+    MX_TRY(w0_arr(S, etarho_cc, nr, true, &d_eta, &h));
+    MX_TRY(w0_arr(S, w0, nr + 1, false, &d_w0, &h_w0));
+    MX_TRY(w0_arr(S, w0_force, nr, false, &d_f, &h_f));
+    void *scratch = nullptr, *pb = nullptr;
+    CUDA_OK(S.alloc(&scratch, sizeof(double) * w0_scratch_doubles(par->nr_fine)));
+    CUDA_OK(S.alloc(&pb, sizeof(double)));
+    w0_planar(*par, d_w0o, d_S, d_p0o, d_p0n, d_g1o, d_g1n, d_pmp, d_eta,
+              const_cast<double*>(d_w0), const_cast<double*>(d_f), static_cast<double*>(scratch),
+              static_cast<double*>(pb), S.stream());
+    CUDA_OK(cudaGetLastError());
+    if (h_w0) CUDA_OK(cudaMemcpyAsync(w0, d_w0, sizeof(double) * (nr + 1), cudaMemcpyDeviceToHost, S.stream()));
+    if (h_f) CUDA_OK(cudaMemcpyAsync(w0_force, d_f, sizeof(double) * nr, cudaMemcpyDeviceToHost, S.stream()));
+    if (par->add_pb && p0bdot)
+        CUDA_OK(cudaMemcpyAsync(p0bdot, pb, sizeof(double), cudaMemcpyDeviceToHost, S.stream()));
+    // Makew0 runs once per time step on a few thousand values: give every caller the
+    // reference's synchronous semantics (p0bdot / host arrays are valid on return)
+    CUDA_OK(cudaStreamSynchronize(S.stream()));
+    return MX_OK;
+}
+
+int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                    const double* rho0_old, const double* rho0_new, const double* p0_old,
+                    const double* p0_new, const double* gamma1bar_old,
+                    const double* gamma1bar_new, const double* p0_minus_peosbar,
+                    const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
+                    const double* r_edge_loc, double* w0, double* w0_force, void* stream) {
+    MX_TRY(check_w0_params(par));
+    MX_TRY(require_device());
+    Session S(stream);
+    const size_t nr = (size_t)par->nr_fine;
+    const double *d_w0o, *d_S, *d_r0o, *d_r0n, *d_p0o, *d_p0n, *d_g1o, *d_g1n, *d_pmp, *d_ecc,
+        *d_eec, *d_rcc, *d_re, *d_w0, *d_f;
+    bool h, h_w0, h_f;
+    MX_TRY(w0_arr(S, w0_old, nr + 1, true, &d_w0o, &h));
+    MX_TRY(w0_arr(S, Sbar, nr, true, &d_S, &h));
+    MX_TRY(w0_arr(S, rho0_old, nr, true, &d_r0o, &h));
+    MX_TRY(w0_arr(S, rho0_new, nr, true, &d_r0n, &h));
+    MX_TRY(w0_arr(S, p0_old, nr, true, &d_p0o, &h));
+    MX_TRY(w0_arr(S, p0_new, nr, true, &d_p0n, &h));
+    MX_TRY(w0_arr(S, gamma1bar_old, nr, true, &d_g1o, &h));
+    MX_TRY(w0_arr(S, gamma1bar_new, nr, true, &d_g1n, &h));
+    MX_TRY(w0_arr(S, p0_minus_peosbar, nr, true, &d_pmp, &h));
+    MX_TRY(w0_arr(S, etarho_cc, nr, true, &d_ecc, &h));
+    MX_TRY(w0_arr(S, etarho_ec, nr + 1, true, &d_eec, &h));
+    MX_TRY(w0_arr(S, r_cc_loc, nr, true, &d_rcc, &h));
+    MX_TRY(w0_arr(S, r_edge_loc, nr + 1, true, &d_re, &h));
+    MX_TRY(w0_arr(S, w0, nr + 1, false, &d_w0, &h_w0));
+    MX_TRY(w0_arr(S, w0_force, nr, false, &d_f, &h_f));
+    void *scratch = nullptr, *st = nullptr;
+    CUDA_OK(S.alloc(&scratch, sizeof(double) * w0_scratch_doubles(par->nr_fine)));
+    CUDA_OK(S.alloc(&st, sizeof(int)));
+    w0_sphr(*par, d_w0o, d_S, d_r0o, d_r0n, d_p0o, d_p0n, d_g1o, d_g1n, d_pmp, d_ecc, d_eec,
+            d_rcc, d_re, const_cast<double*>(d_w0), const_cast<double*>(d_f),
+            static_cast<double*>(scratch), static_cast<int*>(st), S.stream());
+    CUDA_OK(cudaGetLastError());
+    int status = 0;
+    CUDA_OK(cudaMemcpyAsync(&status, st, sizeof(int), cudaMemcpyDeviceToHost, S.stream()));
+    if (h_w0) CUDA_OK(cudaMemcpyAsync(w0, d_w0, sizeof(double) * (nr + 1), cudaMemcpyDeviceToHost, S.stream()));
+    if (h_f) CUDA_OK(cudaMemcpyAsync(w0_force, d_f, sizeof(double) * nr, cudaMemcpyDeviceToHost, S.stream()));
+    CUDA_OK(cudaStreamSynchronize(S.stream()));
+    // the reference aborts here (MaestroMakew0.cpp:950-962); the overlay turns this into Abort
+    if (status == 1) return fail(MX_ERR_INVALID, "tridiag: CAN NOT HAVE B(0) = 0.0");
+    if (status == 2) return fail(MX_ERR_INVALID, "tridiag: TRIDIAG FAILED");
     return MX_OK;
 }
 

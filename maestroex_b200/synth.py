@@ -249,3 +249,73 @@ def make_problem(dim=3, n=(16, 16, 16), nspec=3, ng=3, bc_kind="periodic", seed=
                    force=Fab(force, flo, fhi), umac=umac_f, sedge=sedge, sflux=sflux,
                    etarhoflux=etarho, base=base, mac=mac, dt=dt, rel_eps=rel_eps,
                    bc=bc_set(bc_kind, nscal, dim))
+
+
+# ---------------------------------------------------------------------------------------
+# Makew0 inputs (Source/MaestroMakew0.cpp:5-14): a stratified base state with noise
+# ---------------------------------------------------------------------------------------
+W0_CASES = {
+    # name -> (spherical, nr_fine, base_cutoff_density_coord, is_predictor, add_pb,
+    #          dpdt_factor, base_cutoff_density, seed)
+    "planar_pred": (0, 64, 50, 1, 0, 0.0, -1.0, 1),
+    "planar_corr_pb": (0, 64, 64, 0, 1, 0.3, -1.0, 2),
+    "planar_odd_pb": (0, 257, 200, 1, 1, 0.5, -1.0, 3),
+    "planar_wd": (0, 2218, 1800, 0, 0, 0.2, -1.0, 4),
+    "planar_tiny": (0, 5, 3, 1, 0, 0.1, -1.0, 5),
+    "sphr_small": (1, 64, 50, 1, 0, 0.0, 1.0e4, 6),
+    "sphr_cut_above": (1, 64, 80, 1, 0, 0.3, 1.0e5, 7),
+    "sphr_odd": (1, 257, 200, 1, 0, 0.5, 3.0e4, 8),
+    "sphr_wd": (1, 2218, 1800, 1, 0, 0.2, 1.0e4, 9),
+}
+
+
+def make_w0_problem(name: str):
+    """(W0Params, dict of input arrays) of one Makew0 case."""
+    from .abi import W0Params
+    sph, nr, cut, pred, pb, dpdt, bcd, seed = W0_CASES[name]
+    rng = np.random.default_rng(1000 + seed)
+    dr = (5.0e8 if sph else 1.0e8) / nr
+    z = (np.arange(nr) + 0.5) / nr
+    rho = 1.0e7 * np.exp(-8.0 * z) * (1.0 + 0.01 * rng.random(nr))
+    p0 = 1.0e24 * np.exp(-9.0 * z) * (1.0 + 0.01 * rng.random(nr))
+    g1 = 1.4 + 0.2 * rng.random(nr)
+    d = {
+        "w0_old": 1.0e4 * np.cumsum(rng.standard_normal(nr + 1)) / nr,
+        "Sbar": 1.0e-3 * rng.standard_normal(nr),
+        "rho0_old": rho,
+        "rho0_new": rho * (1.0 + 1.0e-3 * rng.standard_normal(nr)),
+        "p0_old": p0,
+        "p0_new": p0 * (1.0 + 1.0e-3 * rng.standard_normal(nr)),
+        "gamma1bar_old": g1,
+        "gamma1bar_new": g1 + 1.0e-3 * rng.standard_normal(nr),
+        "p0_minus_peosbar": 1.0e18 * rng.standard_normal(nr),
+        "etarho_cc": 1.0e2 * rng.standard_normal(nr),
+        "etarho_ec": 1.0e2 * rng.standard_normal(nr + 1),
+        "r_cc_loc": (np.arange(nr) + 0.5) * dr,
+        "r_edge_loc": np.arange(nr + 1) * dr,
+    }
+    d = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in d.items()}
+    par = W0Params(nr_fine=nr, base_cutoff_density_coord=cut, dr=dr, dt=0.37, dt_in=0.4,
+                   dtold_in=0.33, is_predictor=pred, add_pb=pb, dpdt_factor=dpdt,
+                   base_cutoff_density=bcd)
+    return bool(sph), par, d
+
+
+def run_w0(calls, sph: bool, par, d, xp=np, put=lambda a: a):
+    """Makew0 through `calls`; returns (w0, w0_force, p0bdot).  `put` moves an input array to
+    where the back end wants it (identity for host arrays)."""
+    nr = par.nr_fine
+    w0 = put(np.full(nr + 1, 7.0))
+    force = put(np.full(nr, 7.0))
+    a = {k: put(v) for k, v in d.items()}
+    if sph:
+        calls.make_w0_sphr(par, a["w0_old"], a["Sbar"], a["rho0_old"], a["rho0_new"],
+                           a["p0_old"], a["p0_new"], a["gamma1bar_old"], a["gamma1bar_new"],
+                           a["p0_minus_peosbar"], a["etarho_cc"], a["etarho_ec"],
+                           a["r_cc_loc"], a["r_edge_loc"], w0, force)
+        pb = 0.0
+    else:
+        pb = calls.make_w0_planar(par, a["w0_old"], a["Sbar"], a["p0_old"], a["p0_new"],
+                                  a["gamma1bar_old"], a["gamma1bar_new"],
+                                  a["p0_minus_peosbar"], a["etarho_cc"], w0, force)
+    return w0, force, pb

@@ -7,7 +7,8 @@
  *
  * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks it bit-for-bit against
  * oracle/_ref/libmaestro_ref{2,3}d.so, which is the reference's own
- * Source/Maestro{MakeEdgeScalars,PPM,Slopes,MakeFlux,CelltoEdge}.cpp compiled unmodified
+ * Source/Maestro{MakeEdgeScalars,PPM,Slopes,MakeFlux,CelltoEdge,Makew0,MakeGrav}.cpp compiled
+ * unmodified
  * (oracle/Makefile), and against the golden vectors under tests/golden/ generated from that
  * library (tests/golden/make_golden.py).
  *
@@ -25,9 +26,13 @@
  *   Source/MaestroMakeFlux.cpp:18-465       -> orc_make_rhoX_flux()
  *   Source/MaestroMakeFlux.cpp:467-1067     -> orc_make_rhoh_flux()
  *   Source/MaestroCelltoEdge.cpp:5-55       -> orc_cell_to_edge()
+ *   Source/MaestroMakew0.cpp:5-58,60-272    -> orc_make_w0_planar() (one radial level)
+ *   Source/MaestroMakew0.cpp:537-740,942-969 + Source/MaestroMakeGrav.cpp:303-322
+ *                                           -> orc_make_w0_sphr()
  * Direction-dependent quirks of the reference that are reproduced on purpose are marked
  * "QUIRK" with the file:line they come from.
  */
+#define _GNU_SOURCE /* M_PI under -std=c11 */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1040,5 +1045,145 @@ int orc_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_h
             edge[r] = dmin(dmax(tmp, s0min), s0max);
         }
     }
+    return 0;
+}
+
+/* w0_force, Source/MaestroMakew0.cpp:241-268 (planar) and :727-738 (spherical) */
+static void w0_force_cells(const MxW0Params* p, const double* w0_old, const double* w0,
+                           double* w0_force) {
+    const double dt_in = p->dt_in, dtold_in = p->dtold_in;
+    const double dt_avg = 0.5 * (dt_in + dtold_in);
+    for (int r = 0; r < p->nr_fine; ++r) {
+        double w0_old_cen = 0.5 * (w0_old[r] + w0_old[r + 1]);
+        double w0_new_cen = 0.5 * (w0[r] + w0[r + 1]);
+        double w0_avg = 0.5 * (dt_in * w0_old_cen + dtold_in * w0_new_cen) / dt_avg;
+        double div_avg = 0.5 *
+                         (dt_in * (w0_old[r + 1] - w0_old[r]) + dtold_in * (w0[r + 1] - w0[r])) /
+                         dt_avg;
+        w0_force[r] = (w0_new_cen - w0_old_cen) / dt_avg + w0_avg * div_avg / p->dr;
+    }
+}
+
+/* Maestro::Makew0 -> Makew0Planar, Source/MaestroMakew0.cpp:5-58,60-272; max_radial_level 0,
+ * one chunk [0, nr_fine-1] (RestrictBase / FillGhostBase are no-ops at one level) */
+int orc_make_w0_planar(const MxW0Params* p, const double* w0_old, const double* Sbar,
+                       const double* p0_old, const double* p0_new, const double* g1o,
+                       const double* g1n, const double* pmp, const double* etarho_cc,
+                       double* w0, double* w0_force, double* p0bdot) {
+    const int nr = p->nr_fine, cut = p->base_cutoff_density_coord;
+    const double dr = p->dr;
+    double* psi = (double*)calloc((size_t)nr, sizeof(double));
+    double* int1 = (double*)calloc((size_t)nr + 1, sizeof(double));
+    for (int r = 0; r <= nr; ++r) w0[r] = 0.0;
+    for (int r = 0; r < nr; ++r)
+        if (r < cut) psi[r] = etarho_cc[r] * fabs(p->grav_const); /* :132-139 */
+    w0[0] = 0.0;
+    int1[0] = 0.0;
+    for (int r = 1; r <= nr; ++r) { /* :143-173 */
+        double gamma1bar_p0_avg = (g1o[r - 1] + g1n[r - 1]) * (p0_old[r - 1] + p0_new[r - 1]) / 4.0;
+        double delta_chi_w0 = 0.0;
+        if (r < cut) {
+            if (p->is_predictor) {
+                delta_chi_w0 = p->dpdt_factor * pmp[r - 1] / (g1o[r - 1] * p0_old[r - 1] * p->dt);
+            } else {
+                delta_chi_w0 += p->dpdt_factor * pmp[r - 1] / (g1n[r - 1] * p0_new[r - 1] * p->dt);
+            }
+        }
+        int1[r] = int1[r - 1] + (1.0 / gamma1bar_p0_avg) * dr;
+        w0[r] = w0[r - 1] + Sbar[r - 1] * dr - psi[r - 1] / gamma1bar_p0_avg * dr -
+                delta_chi_w0 * dr;
+    }
+    if (p->add_pb) { /* :175-184 */
+        double pb = w0[nr] / int1[nr];
+        if (p0bdot) *p0bdot = pb;
+        for (int r = 1; r <= nr; ++r) w0[r] -= pb * int1[r];
+    }
+    w0_force_cells(p, w0_old, w0, w0_force);
+    free(psi);
+    free(int1);
+    return 0;
+}
+
+/* Maestro::Makew0 -> Makew0Sphr, Source/MaestroMakew0.cpp:537-740, with MakeGravEdge's
+ * spherical branch (Source/MaestroMakeGrav.cpp:303-322) and Tridiag (:942-969) inlined */
+int orc_make_w0_sphr(const MxW0Params* p, const double* w0_old, const double* Sbar,
+                     const double* rho0_old, const double* rho0_new, const double* p0_old,
+                     const double* p0_new, const double* g1o, const double* g1n,
+                     const double* pmp, const double* etarho_cc, const double* etarho_ec,
+                     const double* rcc, const double* re, double* w0, double* w0_force) {
+    const double Gconst = 6.67428e-8; /* Source/Maestro.H:1864 */
+    const int nr = p->nr_fine;
+    const double dr0 = p->dr, dt_in = p->dt_in;
+    double* buf = (double*)calloc((size_t)(11 * (nr + 2)), sizeof(double));
+    double *g_nph = buf, *p_nph = g_nph + nr + 2, *rho_nph = p_nph + nr + 2,
+           *wS = rho_nph + nr + 2, *grav = wS + nr + 2, *A = grav + nr + 2, *B = A + nr + 2,
+           *C = B + nr + 2, *F = C + nr + 2, *u = F + nr + 2, *gam = u + nr + 2;
+    for (int r = 0; r < nr; ++r) { /* :595-600 */
+        p_nph[r] = 0.5 * (p0_old[r] + p0_new[r]);
+        rho_nph[r] = 0.5 * (rho0_old[r] + rho0_new[r]);
+        g_nph[r] = 0.5 * (g1o[r] + g1n[r]);
+    }
+    wS[0] = 0.0;
+    for (int r = 1; r <= nr; ++r) { /* :608-622 */
+        double volume_discrepancy = rho0_old[r - 1] > p->base_cutoff_density
+                                        ? p->dpdt_factor * pmp[r - 1] / dt_in
+                                        : 0.0;
+        wS[r] = wS[r - 1] + dr0 * Sbar[r - 1] * rcc[r - 1] * rcc[r - 1];
+        if (volume_discrepancy != 0.0) {
+            wS[r] -= dr0 * volume_discrepancy * rcc[r - 1] * rcc[r - 1] /
+                     (g_nph[r - 1] * p_nph[r - 1]);
+        }
+    }
+    for (int r = 1; r <= nr; ++r) wS[r] /= (re[r] * re[r]);
+    /* MakeGravEdge, spherical */
+    grav[0] = 0.0;
+    double mencl = 0.0;
+    for (int r = 1; r <= nr; ++r) {
+        if (rho_nph[r - 1] > p->base_cutoff_density) {
+            mencl += 4.0 / 3.0 * M_PI * (re[r] - re[r - 1]) *
+                     (re[r] * re[r] + re[r] * re[r - 1] + re[r - 1] * re[r - 1]) * rho_nph[r - 1];
+        }
+        grav[r] = -Gconst * mencl / (re[r] * re[r]);
+    }
+    int max_cutoff = p->base_cutoff_density_coord < nr - 1 ? p->base_cutoff_density_coord : nr - 1;
+    for (int r = 1; r <= max_cutoff; ++r) { /* :653-681 */
+        A[r] = g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]);
+        A[r] /= dr0 * dr0;
+        B[r] = -(g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]) +
+                 g_nph[r] * p_nph[r] / (rcc[r] * rcc[r])) /
+               (dr0 * dr0);
+        double dpdr = (p_nph[r] - p_nph[r - 1]) / dr0;
+        B[r] -= 4.0 * dpdr / (re[r] * re[r] * re[r]);
+        C[r] = g_nph[r] * p_nph[r] / (rcc[r] * rcc[r]);
+        C[r] /= dr0 * dr0;
+        F[r] = 4.0 * dpdr * wS[r] / re[r] -
+               grav[r] *
+                   (rcc[r] * rcc[r] * etarho_cc[r] - rcc[r - 1] * rcc[r - 1] * etarho_cc[r - 1]) /
+                   (dr0 * re[r] * re[r]) -
+               4.0 * M_PI * Gconst * 0.5 * (rho_nph[r] + rho_nph[r - 1]) * etarho_ec[r];
+    }
+    A[0] = 0.0; B[0] = 1.0; C[0] = 0.0; F[0] = 0.0;
+    A[max_cutoff + 1] = -1.0; B[max_cutoff + 1] = 1.0; C[max_cutoff + 1] = 0.0;
+    F[max_cutoff + 1] = 0.0;
+    { /* Tridiag(A, B, C, F, u, max_cutoff + 2) */
+        const int n = max_cutoff + 2;
+        if (B[0] == 0) { free(buf); return -1; }
+        double bet = B[0];
+        u[0] = F[0] / bet;
+        for (int j = 1; j < n; j++) {
+            gam[j] = C[j - 1] / bet;
+            bet = B[j] - A[j] * gam[j];
+            if (bet == 0) { free(buf); return -1; }
+            u[j] = (F[j] - A[j] * u[j - 1]) / bet;
+        }
+        for (int j = n - 2; j >= 0; --j) u[j] -= gam[j + 1] * u[j + 1];
+    }
+    w0[0] = wS[0];
+    for (int r = 1; r <= max_cutoff + 1; ++r) w0[r] = u[r] / (re[r] * re[r]) + wS[r];
+    for (int r = max_cutoff + 2; r <= nr; ++r) {
+        w0[r] = w0[max_cutoff + 1] * re[max_cutoff + 1] * re[max_cutoff + 1] / (re[r] * re[r]);
+    }
+    w0_force_cells(p, w0_old, w0, w0_force);
+    free(buf);
     return 0;
 }

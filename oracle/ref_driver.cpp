@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): extern "C" driver around the REFERENCE's own
-// Maestro::MakeEdgeScal / MakeRhoXFlux / MakeRhoHFlux / CelltoEdge, compiled from
+// Maestro::MakeEdgeScal / MakeRhoXFlux / MakeRhoHFlux / CelltoEdge / Makew0, compiled from
 // /root/reference/Source/*.cpp against oracle/shim (see oracle/Makefile) into
 // oracle/_ref/libmaestro_ref{2,3}d.so.  It aliases the caller's flat arrays as single-box
 // MultiFabs and calls the reference member functions unchanged.  Used only by tests/, by
@@ -26,6 +26,10 @@ int ppm_type = 1, slope_order = 4, ppm_trace_forces = 0, bds_type = 0;
 int species_pred_type = 1, enthalpy_pred_type = 1, reflux_type = 1;
 bool spherical = false, use_exact_base_state = false, evolve_base_state = true,
      average_base_state = false;
+int maestro_verbose = 0;
+bool do_2d_planar_octant = false, do_planar_invsq_grav = false, add_pb = false;
+Real base_cutoff_density = -1.0, dpdt_factor = 0.0, planar_invsq_mass = 0.0,
+     grav_const = -1.5e10;
 }  // namespace maestro
 int Rho = 0, RhoH = 1, Temp = 2, Pi = 3, FirstSpec = 4, NumSpec = 3, Nscal = 7;
 
@@ -264,6 +268,110 @@ int DRV(cell_to_edge)(const double* cell, double* edge, int nr, int r_lo, int r_
     m.CelltoEdge(c, e);
     for (int i = 0; i <= nr; ++i) edge[i] = ea(i);
     return 0;
+}
+
+namespace {
+// one radial level, one chunk [0, nr_fine-1]: the base_geom tables Makew0* reads
+struct W0Geom {
+    int nr_tab[1], chunks[1], rs[2], re[2], cut[1];
+    double dr_tab[1];
+    std::vector<double> rcc, redge;
+    void attach(Maestro& m, const MxW0Params* p, const double* r_cc, const double* r_edge) {
+        const int nr = p->nr_fine;
+        nr_tab[0] = nr;
+        chunks[0] = 1;
+        rs[0] = 0; rs[1] = 0;
+        re[0] = 0; re[1] = nr - 1;
+        cut[0] = p->base_cutoff_density_coord;
+        dr_tab[0] = p->dr;
+        rcc.assign(nr, 0.0);
+        redge.assign(nr + 1, 0.0);
+        for (int r = 0; r < nr; ++r) rcc[r] = r_cc ? r_cc[r] : (r + 0.5) * p->dr;
+        for (int r = 0; r <= nr; ++r) redge[r] = r_edge ? r_edge[r] : r * p->dr;
+        auto& bg = m.base_geom;
+        bg.max_radial_level = 0;
+        bg.finest_radial_level = 0;
+        bg.nr_fine = nr;
+        bg.dr_fine = p->dr;
+        bg.nr_irreg = 0;
+        bg.nr.init(nr_tab, 1, 1, 1);
+        bg.dr.init(dr_tab, 1, 1, 1);
+        bg.r_cc_loc.init(rcc.data(), 1, nr, 1);
+        bg.r_edge_loc.init(redge.data(), 1, nr + 1, 1);
+        bg.base_cutoff_density_coord.init(cut, 1, 1, 1);
+        bg.numdisjointchunks.init(chunks, 1, 1, 1);
+        bg.r_start_coord.init(rs, 1, 2, 1);
+        bg.r_end_coord.init(re, 1, 2, 1);
+    }
+};
+
+void fill1(BaseState<Real>& b, const double* src, int len) {
+    b.define(1, len, 1);
+    auto a = b.array();
+    for (int i = 0; i < len; ++i) a(i) = src ? src[i] : 0.0;
+}
+
+int run_w0(bool sphr, const MxW0Params* p, const double* w0_old, const double* Sbar,
+           const double* rho0_old, const double* rho0_new, const double* p0_old,
+           const double* p0_new, const double* g1o, const double* g1n, const double* pmp,
+           const double* etarho_cc, const double* etarho_ec, const double* r_cc,
+           const double* r_edge, double* w0, double* w0_force, double* p0bdot) {
+    Maestro m;
+    W0Geom wg;
+    wg.attach(m, p, r_cc, r_edge);
+    const int nr = p->nr_fine;
+    maestro::spherical = sphr;
+    maestro::use_exact_base_state = false;
+    maestro::do_planar_invsq_grav = false;
+    maestro::do_2d_planar_octant = false;
+    maestro::maestro_verbose = 0;
+    maestro::add_pb = p->add_pb != 0;
+    maestro::grav_const = p->grav_const;
+    maestro::dpdt_factor = p->dpdt_factor;
+    maestro::base_cutoff_density = p->base_cutoff_density;
+    m.dt = p->dt;
+    BaseState<Real> b_w0o, b_force, b_S, b_r0o, b_r0n, b_p0o, b_p0n, b_g1o, b_g1n, b_pmp;
+    fill1(b_w0o, w0_old, nr + 1);
+    fill1(b_force, w0_force, nr);
+    fill1(b_S, Sbar, nr);
+    fill1(b_r0o, rho0_old, nr);
+    fill1(b_r0n, rho0_new, nr);
+    fill1(b_p0o, p0_old, nr);
+    fill1(b_p0n, p0_new, nr);
+    fill1(b_g1o, g1o, nr);
+    fill1(b_g1n, g1n, nr);
+    fill1(b_pmp, pmp, nr);
+    fill1(m.w0, w0, nr + 1);
+    fill1(m.etarho_cc, etarho_cc, nr);
+    fill1(m.etarho_ec, etarho_ec, nr + 1);
+    m.Makew0(b_w0o, b_force, b_S, b_r0o, b_r0n, b_p0o, b_p0n, b_g1o, b_g1n, b_pmp, p->dt_in,
+             p->dtold_in, p->is_predictor != 0);
+    auto wa = m.w0.array();
+    auto fa = b_force.array();
+    for (int r = 0; r <= nr; ++r) w0[r] = wa(r);
+    for (int r = 0; r < nr; ++r) w0_force[r] = fa(r);
+    if (p0bdot && p->add_pb) *p0bdot = m.p0bdot;
+    return 0;
+}
+}  // namespace
+
+// Maestro::Makew0 -> Makew0Planar, Source/MaestroMakew0.cpp:5,60
+int DRV(make_w0_planar)(const MxW0Params* p, const double* w0_old, const double* Sbar,
+                       const double* p0_old, const double* p0_new, const double* g1o,
+                       const double* g1n, const double* pmp, const double* etarho_cc,
+                       double* w0, double* w0_force, double* p0bdot) {
+    return run_w0(false, p, w0_old, Sbar, nullptr, nullptr, p0_old, p0_new, g1o, g1n, pmp,
+                  etarho_cc, nullptr, nullptr, nullptr, w0, w0_force, p0bdot);
+}
+
+// Maestro::Makew0 -> Makew0Sphr, Source/MaestroMakew0.cpp:5,537
+int DRV(make_w0_sphr)(const MxW0Params* p, const double* w0_old, const double* Sbar,
+                     const double* rho0_old, const double* rho0_new, const double* p0_old,
+                     const double* p0_new, const double* g1o, const double* g1n,
+                     const double* pmp, const double* etarho_cc, const double* etarho_ec,
+                     const double* r_cc, const double* r_edge, double* w0, double* w0_force) {
+    return run_w0(true, p, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, g1o, g1n, pmp,
+                  etarho_cc, etarho_ec, r_cc, r_edge, w0, w0_force, nullptr);
 }
 
 }  // extern "C"

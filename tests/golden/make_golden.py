@@ -4,7 +4,7 @@
 Run here (the container that has /root/reference):   python tests/golden/make_golden.py
 Each fixture holds the complete inputs of one small single-box case (state, force, MAC
 velocities, base-state arrays, BC table, dt, rel_eps ...) and the outputs of the reference's
-own Maestro::MakeEdgeScal -> MakeRhoXFlux -> MakeRhoHFlux (and CelltoEdge), obtained from
+own Maestro::MakeEdgeScal -> MakeRhoXFlux -> MakeRhoHFlux (and CelltoEdge, Makew0), obtained from
 oracle/_ref/libmaestro_ref{2,3}d.so = Source/Maestro{MakeEdgeScalars,PPM,Slopes,MakeFlux,
 CelltoEdge}.cpp compiled unmodified (oracle/Makefile).  The fixtures travel to the GPU box,
 the reference does not: tests/test_golden.py checks the C oracle (CPU) and libmxadv.so (GPU)
@@ -90,6 +90,14 @@ def main():
         out[f"edge_{lo}_{hi}"] = edge
     np.savez_compressed(os.path.join(HERE, "cell_to_edge.npz"), cell=cell, **out)
     print("cell_to_edge ok")
+    # Makew0 (Source/MaestroMakew0.cpp + MaestroMakeGrav.cpp compiled unmodified)
+    from maestroex_b200.synth import W0_CASES, make_w0_problem, run_w0
+    for name in W0_CASES:
+        sph, par, d = make_w0_problem(name)
+        w0, force, pb = run_w0(ref, sph, par, d)
+        np.savez_compressed(os.path.join(HERE, "w0_" + name + ".npz"), w0=w0, w0_force=force,
+                            p0bdot=np.float64(pb), **{"in_" + k: v for k, v in d.items()})
+        print("w0", name, "ok")
 
 
 if __name__ == "__main__":
