@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(GX* GY, 1) k_fused(const __grid_constant__ Fus
 
 #include "mx_stream.cuh"
 #include "mx_stream4.cuh"
+#include "mx_stream5.cuh"
 
 template <int PPM, bool BC, int GX, int GY>
 int launch(const FusedArgs& A, cudaStream_t stream) {
@@ -541,6 +542,14 @@ int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
         A.nty = (ny + 13) / 14;
         if (A.zc > ST_MAXZC) A.zc = ST_MAXZC;
         const bool v3 = kv && kv[0] == 'v' && kv[1] == '3';
+        // k_stream5 (two cell rows per thread) is bit-identical but measured 1.2x slower than
+        // k_stream4 on B200: opt-in for A/B runs only
+        const bool v5 = kv && kv[0] == 'v' && kv[1] == '5';
+        if (v5) {
+            if (ppm_type == 0) return launch_stream5_mode<0>(A, stream);
+            if (ppm_type == 1) return launch_stream5_mode<1>(A, stream);
+            return launch_stream5_mode<2>(A, stream);
+        }
         if (!v3) {
             if (ppm_type == 0) return launch_stream4_mode<0>(A, stream);
             if (ppm_type == 1) return launch_stream4_mode<1>(A, stream);

@@ -14,7 +14,8 @@ from .calls import Calls
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libmxadv.so")
+# MXADV_LIB: A/B builds of the same ABI (kernel experiments); default is the in-tree build
+LIB_PATH = os.environ.get("MXADV_LIB") or os.path.join(CSRC, "libmxadv.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mxadv.h")
 
 

@@ -1,0 +1,6 @@
+for zc in 8 16 32; do
+  echo "zc=$zc"
+  MXADV_KERNEL=v4 MXADV_ZCHUNK=$zc python bench.py --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['ms_per_launch'], d['roofline']['frac'])"
+  MXADV_KERNEL=v4 MXADV_ZCHUNK=$zc ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:k_stream4 -s 2 -c 1 --csv --log-file gpurun_out/traffic2_zc$zc.csv python bench.py --size 256 --steps 1 --warmup 1 --no-cpu --no-e2e > /dev/null 2>&1
+  grep -E "dram__bytes|gpu__time|hit_rate" gpurun_out/traffic2_zc$zc.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}'
+done
