@@ -261,7 +261,7 @@ def run_mxadv(a):
     updates_per_step = zones * (a.nspec + 2) * world
     value = updates_per_step / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_fused, density mode): algorithmic bytes / launch
+    # ---- roofline of the dominant kernel (k_stream4, density mode): algorithmic bytes / launch
     bytes_density = zones * (64 * (a.nspec + 1) + 32)  # SURVEY.md 8(d), DESIGN.md section 4
     peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -280,7 +280,8 @@ def run_mxadv(a):
             traffic = json.load(open(tj)).get(key)
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_fused (density pass: nspec+1 edge states + fluxes)",
+    roofline = {"bound": "hbm",
+                "kernel": f"k_stream4<{a.ppm},1> (density pass: nspec+1 edge states + fluxes)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_density, "ms_per_launch": ms_density}
