@@ -260,6 +260,18 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             const int it = a - a0;
             const double* pa = ring + ((it + LA) & (S4_NS - 1)) * PL + rc;  // plane a, my cell
             // ---- P0: current-plane registers, prefetch of the next plane ----------------
+#ifdef MX_EXP_FAKEIN
+            // experiment (wrong results): velocities / force read from a shared-memory plane as a
+            // loader warp would provide them -> no input pointers, prefetch or rotation registers
+            const double* fk = tab + (it & 3);
+            const double um = fk[tid & 63], up = fk[(tid & 63) + 1], vm = fk[(tid & 31) + 2],
+                         vp = fk[(tid & 31) + 34], f0 = fk[(tid & 15) + 7];
+            w_m1 = fk[(tid & 31) + 3];
+            w_0 = fk[(tid & 31) + 4];
+            w_p1 = fk[(tid & 31) + 5];
+            if (a < k1) stage_plane((it + 2 * LA + 1) & (S4_NS - 1));
+            if (false) {
+#else
             const double um = um_n, vm = vm_n, vp = vp_n, f0 = f_n;
             double up = shfl_dn1(um);
             if (lane31) up = up31_n;
@@ -268,6 +280,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             w_p1 = w_n;
             if (a < k1) {  // block uniform
                 stage_plane((it + 2 * LA + 1) & (S4_NS - 1));  // plane a+LA+1
+#endif
                 pU += u_sz;
                 pV += v_sz;
                 pW += w_sz;
