@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--nspec", type=int, default=13)
     ap.add_argument("--ppm", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--bc", default="reacting_bubble")
+    ap.add_argument("--spherical", action="store_true",
+                    help="wdconvect-like: spherical flux forms (r0mac / h0mac face arrays)")
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU-baseline sample box")
     ap.add_argument("--e2e-n", type=int, default=128, help="edge of the host-buffer e2e boxes")
     ap.add_argument("--e2e-boxes", type=int, default=8)
@@ -54,7 +56,7 @@ def parse():
 
 def workload_name(a):
     return (f"synthetic uniform {a.n}^3 brick/GPU, nspec {a.nspec} (Nscal {a.nspec + 4}), "
-            f"ppm_type {a.ppm}, planar base state, BCs {a.bc}")
+            f"ppm_type {a.ppm}, {'spherical' if a.spherical else 'planar'} base state, BCs {a.bc}")
 
 
 # ------------------------------------------------------------------------------------------
@@ -125,16 +127,17 @@ def cpu_backend():
     return orc, "port", int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
 
 
-def cpu_step(calls, prob, ppm):
+def cpu_step(calls, prob, ppm, spherical=False):
     """density pass + enthalpy pass with the separate reference member functions."""
     from common import run_edge, run_rhoh, run_rhoX
     from maestroex_b200.synth import FIRSTSPEC, RHO, RHOH
     sedge = run_edge(calls, prob, prob.edge_params(FIRSTSPEC, prob.nspec, ppm_type=ppm),
                      sedge=prob.sedge)
     run_edge(calls, prob, prob.edge_params(RHO, 1, ppm_type=ppm), sedge=sedge)
-    run_rhoX(calls, prob, sedge, prob.flux_params())
+    fpar = prob.flux_params(spherical=1 if spherical else 0)
+    run_rhoX(calls, prob, sedge, fpar)
     run_edge(calls, prob, prob.edge_params(RHOH, 1, ppm_type=ppm), sedge=sedge)
-    run_rhoh(calls, prob, sedge, prob.flux_params())
+    run_rhoh(calls, prob, sedge, fpar)
 
 
 def cpu_measure(a, steps, warmup):
@@ -142,12 +145,12 @@ def cpu_measure(a, steps, warmup):
     calls, kind, cores = cpu_backend()
     n = a.cpu_n
     prob = make_problem(dim=3, n=(n, n, n), nspec=a.nspec, ng=4 if a.ppm == 2 else 3,
-                        bc_kind=a.bc, seed=7)
+                        bc_kind=a.bc, seed=7, spherical=a.spherical)
     for _ in range(warmup):
-        cpu_step(calls, prob, a.ppm)
+        cpu_step(calls, prob, a.ppm, a.spherical)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(calls, prob, a.ppm)
+        cpu_step(calls, prob, a.ppm, a.spherical)
     dt = (time.perf_counter() - t0) / steps
     updates = n ** 3 * (a.nspec + 2)
     return {"value": updates / dt, "unit": UNIT, "cores": cores, "kind": kind,
@@ -206,12 +209,28 @@ def run_mxadv(a):
     prob = make_device_problem(n=(n, n, n), nspec=a.nspec, ng=ng, bc_kind=a.bc,
                                seed=20240807 + rank, device=str(dev),
                                dom_n=tuple(n * pg[d] for d in range(3)),
-                               valid_lo=tuple(n * coord[d] for d in range(3)))
+                               valid_lo=tuple(n * coord[d] for d in range(3)),
+                               spherical=a.spherical)
     outputs = (prob.sedge, prob.sflux, prob.etarhoflux)
     epar_d = prob.edge_params(FIRSTSPEC, a.nspec, ppm_type=a.ppm)
     epar_h = prob.edge_params(RHOH, 1, ppm_type=a.ppm)
-    fpar = prob.flux_params()
+    fpar = prob.flux_params(spherical=1 if a.spherical else 0)
     stream = torch.cuda.current_stream().cuda_stream
+
+    def enthalpy_pass():
+        if not a.spherical:
+            enthalpy_edge_flux(calls, prob, epar_h, fpar, outputs=outputs, stream=stream)
+            return
+        # spherical: the fused enthalpy entry point is planar only; the same two reference
+        # calls separately (MakeEdgeScal -> fused MODE-0 kernel, MakeRhoHFlux -> flux kernel)
+        b, m = prob.base, prob.mac
+        calls.make_edge_scal(prob.geom, prob.state, prob.sedge, prob.umac, prob.force, epar_h,
+                             stream)
+        calls.make_rhoh_flux(prob.geom, prob.sflux, prob.sedge, prob.umac, b["rho0_old"],
+                             b["rho0_edge_old"], m["r0mac_old"], b["rho0_new"],
+                             b["rho0_edge_new"], m["r0mac_new"], b["rhoh0_old"],
+                             b["rhoh0_edge_old"], None, b["rhoh0_new"], b["rhoh0_edge_new"],
+                             None, m["h0mac_old"], m["h0mac_new"], fpar, stream)
 
     halo = None
     if world > 1 and not a.no_halo:
@@ -228,7 +247,7 @@ def run_mxadv(a):
             ev[1].record()
         if halo is not None:
             halo.exchange([RHOH], stream)
-        enthalpy_edge_flux(calls, prob, epar_h, fpar, outputs=outputs, stream=stream)
+        enthalpy_pass()
 
     def barrier():
         if world > 1:
@@ -288,7 +307,7 @@ def run_mxadv(a):
 
     # ---- e2e: the same passes through the C ABI with pinned HOST fabs (library stages them)
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and not a.spherical:
         en = a.e2e_n
         dsmall = make_device_problem(n=(en, en, en), nspec=a.nspec, ng=ng, bc_kind=a.bc,
                                      seed=99 + rank, device=str(dev))

@@ -568,8 +568,19 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
     }
     KEdge e = make_kedge(epar);
     if (fused_density_supported(kg, e, f)) {
+        // spherical: the time-centred rho0 on faces is species independent; form it once
+        // (3 x 8 B/zone of workspace) instead of twice per face and species inside the kernel
+        double* r0e[3] = {nullptr, nullptr, nullptr};
+        if (sph) {
+            for (int d = 0; d < 3; ++d) {
+                void* p = nullptr;
+                CUDA_OK(S.alloc(&p, sizeof(double) * (size_t)a.sedge[d].sn));
+                r0e[d] = static_cast<double*>(p);
+                mac_average(kg, d, mac.r0_old[d], mac.r0_new[d], a.sedge[d], r0e[d], S.stream());
+            }
+        }
         const int rc = fused_density(kg, e, epar, rho_bccomp, f, a.state, a.sedge, sf, eta, a.umac,
-                                     a.force, mac, S.stream());
+                                     a.force, mac, sph ? r0e : nullptr, S.stream());
         if (rc == 0) return S.finish();
         if (rc < 0) return fail(MX_ERR_CUDA, "fused density kernel launch failed");
     }

@@ -208,6 +208,31 @@ void flux_rhoh(const KGeom& g, const KFlux& f, const DFab* sflux, const DFab* se
     }
 }
 
+namespace {
+// time-centred spherical base density on the faces of direction d, 0.5*old + 0.5*new exactly as
+// Source/MaestroMakeFlux.cpp:316-318 forms it per face and species, written once per call in
+// the layout of one sedge[d] component so that the fused kernel reads it with the offsets it
+// already has
+__global__ void k_mac_average(KGeom g, int d, DFab r0o, DFab r0n, DFab like, double* out) {
+    const int nx = g.vhi[0] - g.vlo[0] + 1 + (d == 0), ny = g.vhi[1] - g.vlo[1] + 1 + (d == 1);
+    const int nz = g.vhi[2] - g.vlo[2] + 1 + (d == 2);
+    const long tot = (long)nx * ny * nz;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot;
+         t += (long)gridDim.x * blockDim.x) {
+        const int i = g.vlo[0] + (int)(t % nx);
+        const int j = g.vlo[1] + (int)((t / nx) % ny);
+        const int k = g.vlo[2] + (int)(t / ((long)nx * ny));
+        out[like.off(i, j, k)] = 0.5 * r0o.p[r0o.off(i, j, k)] + 0.5 * r0n.p[r0n.off(i, j, k)];
+    }
+}
+}  // namespace
+
+void mac_average(const KGeom& g, int d, const DFab& r0o, const DFab& r0n, const DFab& like,
+                 double* out, cudaStream_t stream) {
+    k_mac_average<<<148 * 8, 256, 0, stream>>>(g, d, r0o, r0n, like, out);
+    mx_count_launch();
+}
+
 void cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi,
                   cudaStream_t stream) {
     const int lo = r_lo, hi = r_hi + 1;

@@ -12,6 +12,9 @@ void flux_rhoX(const KGeom& g, const KFlux& f, const DFab* sflux, const DFab& et
                const DFab* sedge, const DFab* umac, const KMac& mac, cudaStream_t stream);
 void flux_rhoh(const KGeom& g, const KFlux& f, const DFab* sflux, const DFab* sedge,
                const DFab* umac, const KMac& mac, cudaStream_t stream);
+// out[like.off(face)] = 0.5*r0o + 0.5*r0n over the valid faces of direction d
+void mac_average(const KGeom& g, int d, const DFab& r0o, const DFab& r0n, const DFab& like,
+                 double* out, cudaStream_t stream);
 void cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi,
                   cudaStream_t stream);
 void halo_pack(const KGeom& g, const DFab& fab, int dir, int side, int ng, int comp0, int ncomp,

@@ -45,6 +45,7 @@ struct FusedArgs {
     int slope_order;
     DFab state, force, sedge[3], umac[3], sflux[3], eta;
     DFab r0o[3], r0n[3];
+    double* r0e[3];  // spherical: 0.5*(r0mac_old + r0mac_new) laid out like one sedge[d] component
     int ncomp;
     int comp[MAXC];
     int bclo[MAXC][3], bchi[MAXC][3];
@@ -53,9 +54,30 @@ struct FusedArgs {
     KFlux f;
     int do_eta;
     int zc;        // z planes per chunk
+    int zs_lo, zs_hi;  // planes in the short first / last chunk (0: none), see set_zchunks
+    int nzc;           // number of z chunks
     int ntx, nty;  // number of tiles
     int bcdir[3];  // some swept component has a non-interior BC in this direction
 };
+
+// z range [k0, k1) of chunk c.  Where a swept component has a physical BC on a vertical domain
+// face the box touches, the four planes next to that face form their own short chunk, so that
+// only those blocks run the BC instantiation of the streaming kernels (which is ~20 % slower)
+// and every other chunk of the column runs the BC-free one.
+__device__ __forceinline__ void chunk_range(const FusedArgs& A, int c, int& k0, int& k1) {
+    const int vlo = A.g.vlo[2], vend = A.g.vhi[2] + 1;
+    const int mlo = vlo + A.zs_lo, mhi = vend - A.zs_hi;
+    if (A.zs_lo && c == 0) {
+        k0 = vlo;
+        k1 = mlo;
+    } else if (A.zs_hi && c == A.nzc - 1) {
+        k0 = mhi;
+        k1 = vend;
+    } else {
+        k0 = mlo + (c - (A.zs_lo ? 1 : 0)) * A.zc;
+        k1 = min(k0 + A.zc, mhi);
+    }
+}
 
 template <int D>
 __device__ __forceinline__ double over_h(const FusedArgs& A, double x) {
@@ -533,6 +555,18 @@ bool stream_ok(const FusedArgs& A) {
     return ok;
 }
 
+// chunking of the z range (see chunk_range): short boundary chunks only for k_stream4/5
+void set_zchunks(FusedArgs& A, bool allow_short) {
+    const int nz = A.g.vhi[2] - A.g.vlo[2] + 1;
+    A.zs_lo = A.zs_hi = 0;
+    if (allow_short && A.bcdir[2] && nz > 8 + A.zc / 2 && !getenv("MXADV_NO_SHORT_CHUNKS")) {
+        if (A.g.vlo[2] <= A.g.dlo[2] + 3) A.zs_lo = 4;
+        if (A.g.vhi[2] >= A.g.dhi[2] - 3) A.zs_hi = 4;
+    }
+    const int mid = nz - A.zs_lo - A.zs_hi;
+    A.nzc = (mid + A.zc - 1) / A.zc + (A.zs_lo ? 1 : 0) + (A.zs_hi ? 1 : 0);
+}
+
 int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
     const int nx = A.g.vhi[0] - A.g.vlo[0] + 1, ny = A.g.vhi[1] - A.g.vlo[1] + 1;
     const char* kv = getenv("MXADV_KERNEL");
@@ -541,6 +575,7 @@ int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
         A.ntx = (nx + 29) / 30;
         A.nty = (ny + 13) / 14;
         if (A.zc > ST_MAXZC) A.zc = ST_MAXZC;
+        set_zchunks(A, !(kv && kv[0] == 'v' && kv[1] == '3'));
         const bool v3 = kv && kv[0] == 'v' && kv[1] == '3';
         // k_stream5 (two cell rows per thread) is bit-identical but measured 1.2x slower than
         // k_stream4 on B200: opt-in for A/B runs only
@@ -658,7 +693,7 @@ bool fused_density_supported(const KGeom& g, const KEdge& e, const KFlux& f) {
 int fused_density(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, int rho_bccomp,
                   const KFlux& f, const DFab& state, const DFab* sedge, const DFab* sflux,
                   const DFab& etarho, const DFab* umac, const DFab& force, const KMac& mac,
-                  cudaStream_t stream) {
+                  double* const* r0e, cudaStream_t stream) {
     bool any_bc = false;
     if (!comps_ok(par, par->start_bccomp, par->num_comp, &any_bc)) return 1;
     if (!comps_ok(par, rho_bccomp, 1, &any_bc)) return 1;
@@ -673,6 +708,7 @@ int fused_density(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, int 
         A.sflux[d] = sflux[d];
         A.r0o[d] = mac.r0_old[d];
         A.r0n[d] = mac.r0_new[d];
+        A.r0e[d] = r0e ? r0e[d] : nullptr;
     }
     A.ncomp = par->num_comp + 1;
     for (int n = 0; n < A.ncomp; ++n) {

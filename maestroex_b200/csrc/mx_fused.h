@@ -11,6 +11,7 @@ bool fused_density_supported(const KGeom& g, const KEdge& e, const KFlux& f);
 int fused_density(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, int rho_bccomp,
                   const KFlux& f, const DFab& state, const DFab* sedge, const DFab* sflux,
                   const DFab& etarho, const DFab* umac, const DFab& force, const KMac& mac,
+                  double* const* r0e /*[3], spherical: mac_average output, else null*/,
                   cudaStream_t stream);
 bool fused_enthalpy_supported(const KGeom& g, const KEdge& e, const KFlux& f);
 int fused_enthalpy(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, const KFlux& f,

@@ -64,8 +64,8 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     const int x0 = g.vlo[0] + bx * BX, y0 = g.vlo[1] + by * BY;
     const int thx = min(x0 + BX - 1, g.vhi[0]), thy = min(y0 + BY - 1, g.vhi[1]);
     const int i = x0 - 1 + tx, j = y0 - 1 + ty;
-    const int k0 = g.vlo[2] + blockIdx.y * A.zc;
-    const int k1 = min(k0 + A.zc, g.vhi[2] + 1);  // exclusive
+    int k0, k1;  // this block's z chunk, k1 exclusive
+    chunk_range(A, blockIdx.y, k0, k1);
     const bool last = (k1 == g.vhi[2] + 1);
     const int a0 = k0 - 1;
 
@@ -187,6 +187,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
         double* __restrict__ pFz = nullptr;
         double* __restrict__ pEta = nullptr;
         long dRx = 0, dRy = 0, dRz = 0, dGx = 0, dGy = 0, dGz = 0;  // rho comp - this comp
+        long dQx = 0, dQy = 0, dQz = 0;  // spherical: r0e - this comp of sedge
         if (MODE != 0) {
             pFx = A.sflux[0].comp(comp) + fx_c;
             pFy = A.sflux[1].comp(comp) + fy_c;
@@ -195,6 +196,11 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             dRy = (long)(F_.rho - comp) * A.sedge[1].sn;
             dRz = (long)(F_.rho - comp) * A.sedge[2].sn;
             if (MODE == 1) {
+                if (sph) {
+                    dQx = A.r0e[0] - A.sedge[0].comp(comp);
+                    dQy = A.r0e[1] - A.sedge[1].comp(comp);
+                    dQz = A.r0e[2] - A.sedge[2].comp(comp);
+                }
                 dGx = (long)(F_.rho - comp) * A.sflux[0].sn;
                 dGy = (long)(F_.rho - comp) * A.sflux[1].sn;
                 dGz = (long)(F_.rho - comp) * A.sflux[2].sn;
@@ -432,6 +438,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             const bool do_xy = a > k0;                         // x/y faces of plane a-1 exist
             const bool do_z = a >= k0 && (a < k1 || last);     // z face a belongs to this chunk
             double r_x = 0.0, r_y = 0.0, r_z = 0.0, g_x = 0.0, g_y = 0.0, g_z = 0.0, e_z = 0.0;
+            double q_x = 0.0, q_y = 0.0, q_z = 0.0;
             if ((MODE == 1 && flux1) || MODE == 2) {
                 if (need_ser) {
                     if (do_xy) {
@@ -448,6 +455,13 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                     if (do_z) g_z = pFz[dGz];
                 }
                 if (MODE == 1 && A.do_eta && do_z) e_z = pEta[0];
+                if (MODE == 1 && sph) {  // time-centred rho0 on this face (mac_average output)
+                    if (do_xy) {
+                        q_x = pEx[dQx];
+                        q_y = pEy[dQy];
+                    }
+                    if (do_z) q_z = pEz[dQz];
+                }
             }
             __syncthreads();  // S4
 
@@ -525,11 +539,8 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                     // MakeRhoXFlux, MaestroMakeFlux.cpp:191-306 (planar) / :316-407 (spherical)
                     double r0x, r0y;
                     if (sph) {
-                        const int p = a - 1;
-                        r0x = 0.5 * A.r0o[0].p[A.r0o[0].off(icx, jcx, p)] +
-                              0.5 * A.r0n[0].p[A.r0n[0].off(icx, jcx, p)];
-                        r0y = 0.5 * A.r0o[1].p[A.r0o[1].off(icy, jcy, p)] +
-                              0.5 * A.r0n[1].p[A.r0n[1].off(icy, jcy, p)];
+                        r0x = q_x;
+                        r0y = q_y;
                     } else {
                         r0x = r0y = T_RXY[it - 1];
                     }
@@ -561,8 +572,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                 if (MODE == 1 && flux1) {
                     double r0z;
                     if (sph) {
-                        r0z = 0.5 * A.r0o[2].p[A.r0o[2].off(icz, jcz, a)] +
-                              0.5 * A.r0n[2].p[A.r0n[2].off(icz, jcz, a)];
+                        r0z = q_z;
                     } else {
                         r0z = T_RZ[it];
                     }
@@ -625,11 +635,12 @@ __global__ void __launch_bounds__(512, 1) k_stream4(const __grid_constant__ Fuse
     const KGeom& g = A.g;
     const int bx = blockIdx.x % A.ntx, by = blockIdx.x / A.ntx;
     const int x0 = g.vlo[0] + bx * BX, y0 = g.vlo[1] + by * BY;
-    const int k0 = g.vlo[2] + blockIdx.y * A.zc;
+    int k0, k1;
+    chunk_range(A, blockIdx.y, k0, k1);
     bool bc = false;
     if (A.bcdir[0]) bc |= (x0 - 1 <= g.dlo[0] + 2) || (x0 + BX >= g.dhi[0] - 2);
     if (A.bcdir[1]) bc |= (y0 - 1 <= g.dlo[1] + 2) || (y0 + BY >= g.dhi[1] - 2);
-    if (A.bcdir[2]) bc |= (k0 - 1 <= g.dlo[2] + 2) || (k0 + A.zc >= g.dhi[2] - 2);
+    if (A.bcdir[2]) bc |= (k0 - 1 <= g.dlo[2] + 2) || (k1 >= g.dhi[2] - 2);
     if (bc)
         stream4_body<PPM, true, MODE>(A, sm);
     else
@@ -646,8 +657,7 @@ int launch_stream4(const FusedArgs& A, cudaStream_t stream) {
             return -1;
         attr_set = true;
     }
-    const int nz = A.g.vhi[2] - A.g.vlo[2] + 1;
-    dim3 grid(A.ntx * A.nty, (nz + A.zc - 1) / A.zc);
+    dim3 grid(A.ntx * A.nty, A.nzc);
     k_stream4<PPM, MODE><<<grid, 512, smem, stream>>>(A);
     mx_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -147,7 +147,9 @@ def make_device_problem(n=(64, 64, 64), nspec=3, ng=3, bc_kind="reacting_bubble"
 
     mac: Dict[str, List[Fab]] = {}
     if spherical:
-        for name, scale in (("r0mac_old", 1.0e6), ("r0mac_new", 1.0e6)):
+        # what the spherical flux forms read (MaestroMakeFlux.cpp:311-407, :871-1021)
+        for name, scale in (("r0mac_old", 1.0e6), ("r0mac_new", 1.0e6), ("h0mac_old", 1.0e8),
+                            ("h0mac_new", 1.0e8)):
             lst = []
             for d in range(3):
                 lo, hi = geom.face_box(d, 1)

@@ -184,6 +184,39 @@ def test_fused_density_pass(mx, oracle_calls, ppm, bck, spt, nspec, n, residency
     assert_same(geta.data, want_eta.data, "fused etarhoflux", TOL)
 
 
+@pytest.mark.parametrize("residency", ["host", "device"])
+@pytest.mark.parametrize("ppm,spt,nspec,n,kernel", [
+    (1, 1, 3, (37, 19, 23), None),
+    (0, 1, 13, (33, 33, 12), None),
+    (2, 3, 4, (20, 18, 40), None),
+    (1, 1, 5, (31, 29, 35), "v5"),
+])
+def test_fused_density_pass_spherical(mx, oracle_calls, ppm, spt, nspec, n, kernel, residency,
+                                      monkeypatch):
+    """wdconvect-like: spherical flux form (r0mac face arrays, no etarhoflux), outflow BCs;
+    the time-centred rho0 on faces is pre-averaged by the library (mac_average)."""
+    from gpu_util import to_device, to_host
+    from maestroex_b200.fusedcalls import density_edge_flux
+    if kernel:
+        monkeypatch.setenv("MXADV_KERNEL", kernel)
+    ng = 4 if ppm == 2 else 3
+    prob = make_problem(dim=3, n=n, nspec=nspec, ng=ng, bc_kind="outflow", seed=77, spherical=True)
+    epar = prob.edge_params(FIRSTSPEC, nspec, ppm_type=ppm)
+    fpar = prob.flux_params(species_pred_type=spt, spherical=1)
+    want_e = run_edge(oracle_calls, prob, epar)
+    run_edge(oracle_calls, prob, prob.edge_params(RHO, 1, ppm_type=ppm), sedge=want_e)
+    want_f, want_eta = run_rhoX(oracle_calls, prob, want_e, fpar)
+    if residency == "host":
+        ge, gf, geta = density_edge_flux(mx, prob, epar, fpar)
+    else:
+        ge, gf, geta = density_edge_flux(mx, to_device(prob), epar, fpar)
+        ge, gf, geta = to_host(ge), to_host(gf), to_host([geta])[0]
+    comps = [RHO] + list(range(FIRSTSPEC, FIRSTSPEC + nspec))
+    compare_faces(ge, want_e, comps, "fused spherical sedge", TOL)
+    compare_faces(gf, want_f, comps, "fused spherical sflux", TOL)
+    assert np.array_equal(geta.data, want_eta.data)  # spherical: etarhoflux is not touched
+
+
 @pytest.mark.parametrize("ppm,ept,cons", [(1, 1, 0), (2, 1, 0), (0, 1, 0), (1, 0, 1), (1, 2, 0)])
 def test_fused_enthalpy_pass(mx, oracle_calls, ppm, ept, cons):
     from gpu_util import to_device, to_host
