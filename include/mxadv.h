@@ -263,6 +263,37 @@ int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* S
                     const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
                     const double* r_edge_loc, double* w0, double* w0_force, void* stream);
 
+/* ---- Maestro::UpdateScal ------------------------------------
+ * Parameters read by the per-box body of Maestro::UpdateScal
+ * (Source/MaestroAdvection.cpp:86-251; dt = the Maestro member, base_cutoff_density and
+ * do_eos_h_above_cutoff = Source/param/_cpp_parameters). */
+typedef struct MxUpdateParams {
+    double dt;
+    double base_cutoff_density;
+    int do_eos_h_above_cutoff;
+    int rho_comp, rhoh_comp, temp_comp, first_spec, num_spec; /* Rho, RhoH, Temp, FirstSpec, NumSpec */
+    int start_comp; /* RhoH (enthalpy update) or FirstSpec (species + density update) */
+    int num_comp;   /* as passed by the caller; the reference ignores it for both branches */
+} MxUpdateParams;
+
+/* Replaces the zone loop of Maestro::UpdateScal for ONE box (2-D or 3-D, no aux variables):
+ *   start_comp == FirstSpec: (rho X)_k^new = (rho X)_k^old + dt (-div F_k + force_k), then
+ *       rho^new = rho^old + sum_k ((rho X)_k^new - (rho X)_k^old), the density floor at
+ *       base_cutoff_density / 2 and the redistribution of negative species (:186-251);
+ *   start_comp == RhoH: (rho h)^new = (rho h)^old + dt (-div F + force) (:117-135).
+ * stateold / statenew: Nscal components, any (equal or different) ghost widths; sflux[d]:
+ * face centred; force: Nscal components.  Only valid zones of statenew are written.
+ * The EOS call the reference makes for zones with rho^new <= base_cutoff_density when
+ * do_eos_h_above_cutoff (:137-159) is third-party Microphysics code and stays with the
+ * caller: those zones are flagged in eos_mask (one byte per valid zone, i fastest, 1 = the
+ * caller must overwrite statenew(RhoH) with rho * h_eos; required when the flag is set, may
+ * be host or device memory) and counted in *n_eos (HOST pointer, may be NULL).  Reflux /
+ * AverageDown / FillPatch at the end of UpdateScal (:257-296) remain the caller's. */
+int mx_update_scal(const MxGeom* geom, const MxFab* stateold, const MxFab* statenew,
+                   const MxFab* sflux /*[dim]*/, const MxFab* force,
+                   const MxUpdateParams* par, unsigned char* eos_mask, long long* n_eos,
+                   void* stream);
+
 /* ---- ghost-cell exchange between the bricks of one box (multi-GPU) -----------------------
  * Packs / unpacks the `ng`-deep face slab `side` (0 = lo, 1 = hi) of direction `dir` of
  * components [comp0, comp0+ncomp) of a fab into / from a contiguous device buffer, i.e. the

@@ -90,6 +90,21 @@ class MxW0Params(C.Structure):
     ]
 
 
+class MxUpdateParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("base_cutoff_density", C.c_double),
+        ("do_eos_h_above_cutoff", C.c_int),
+        ("rho_comp", C.c_int),
+        ("rhoh_comp", C.c_int),
+        ("temp_comp", C.c_int),
+        ("first_spec", C.c_int),
+        ("num_spec", C.c_int),
+        ("start_comp", C.c_int),
+        ("num_comp", C.c_int),
+    ]
+
+
 # AMReX BCType codes (external/amrex/Src/Base/AMReX_BC_TYPES.H:68-76)
 BC_REFLECT_ODD, BC_INT_DIR, BC_REFLECT_EVEN, BC_FOEXTRAP, BC_EXT_DIR, BC_HOEXTRAP = -1, 0, 1, 2, 3, 4
 
@@ -267,6 +282,28 @@ class W0Params:
     def c(self) -> MxW0Params:
         p = MxW0Params()
         for name, typ in MxW0Params._fields_:
+            v = getattr(self, name)
+            setattr(p, name, int(v) if typ is C.c_int else float(v))
+        return p
+
+
+@dataclass
+class UpdateParams:
+    """Parameters of Maestro::UpdateScal (Source/MaestroAdvection.cpp:86-91)."""
+    dt: float
+    start_comp: int
+    num_comp: int
+    num_spec: int
+    base_cutoff_density: float = -1.0
+    do_eos_h_above_cutoff: int = 1
+    rho_comp: int = 0
+    rhoh_comp: int = 1
+    temp_comp: int = 2
+    first_spec: int = 4
+
+    def c(self) -> MxUpdateParams:
+        p = MxUpdateParams()
+        for name, typ in MxUpdateParams._fields_:
             v = getattr(self, name)
             setattr(p, name, int(v) if typ is C.c_int else float(v))
         return p

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-from .abi import Base, EdgeParams, Fab, FluxParams, Geom, fab_array
+from .abi import Base, EdgeParams, Fab, FluxParams, Geom, fab_array  # noqa: F401
 
 
 class MxError(RuntimeError):
@@ -125,3 +125,25 @@ class Calls:
             v(gamma1bar_old), v(gamma1bar_new), v(p0_minus_peosbar), v(etarho_cc),
             v(etarho_ec), v(r_cc_loc), v(r_edge_loc), v(w0), v(w0_force), *self._tail(stream))
         self._check(rc, "make_w0_sphr")
+
+    # -- Maestro::UpdateScal ----------------------------------------------------------
+    def update_scal(self, geom: Geom, stateold: Fab, statenew: Fab, sflux, force: Fab, par,
+                    eos_mask=None, p0_cart: Fab = None, stream: int = 0):
+        """Zone loop of UpdateScal.  Product / oracle (``mx_`` / ``orc_``): the zones that need
+        the caller's EOS are flagged in ``eos_mask`` (uint8, one per valid zone) and their
+        number is returned.  Compiled reference / overlay (``ref_`` / ``ovl_``): the whole
+        member function incl. its EOS call, ``p0_cart`` required, returns None."""
+        g, so, sn, fo, p = geom.c(), stateold.c(), statenew.c(), force.c(), par.c()
+        if self.prefix in ("ref_", "ovl_"):
+            p0 = p0_cart.c() if p0_cart is not None else None
+            rc = self._fn("update_scal")(C.byref(g), C.byref(so), C.byref(sn),
+                                         self._faces(sflux), C.byref(fo),
+                                         C.byref(p0) if p0 is not None else None, C.byref(p))
+            self._check(rc, "update_scal")
+            return None
+        n = C.c_longlong(0)
+        rc = self._fn("update_scal")(C.byref(g), C.byref(so), C.byref(sn), self._faces(sflux),
+                                     C.byref(fo), C.byref(p), self._vp(eos_mask), C.byref(n),
+                                     *self._tail(stream))
+        self._check(rc, "update_scal")
+        return n.value

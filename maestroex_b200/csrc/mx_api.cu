@@ -12,6 +12,7 @@
 #include "mx_common.h"
 #include "mx_flux.h"
 #include "mx_w0.h"
+#include "mx_update.h"
 #include "mx_fused.h"
 #include "mx_staged.h"
 
@@ -787,6 +788,75 @@ int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* S
     if (status == 1) return fail(MX_ERR_INVALID, "tridiag: CAN NOT HAVE B(0) = 0.0");
     if (status == 2) return fail(MX_ERR_INVALID, "tridiag: TRIDIAG FAILED");
     return MX_OK;
+}
+
+// ---- Maestro::UpdateScal --------------------------------------------------------------
+int mx_update_scal(const MxGeom* geom, const MxFab* stateold, const MxFab* statenew,
+                   const MxFab* sflux, const MxFab* force, const MxUpdateParams* par,
+                   unsigned char* eos_mask, long long* n_eos, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!stateold || !statenew || !sflux || !force || !par)
+        return fail(MX_ERR_INVALID, "null argument");
+    if (par->start_comp != par->rhoh_comp && par->start_comp != par->first_spec)
+        return fail(MX_ERR_INVALID, "Invalid scalar in UpdateScal().");  // :253
+    if (par->num_spec < 1 || par->first_spec < 0 ||
+        par->first_spec + par->num_spec > stateold->ncomp || statenew->ncomp != stateold->ncomp ||
+        force->ncomp < stateold->ncomp)
+        return fail(MX_ERR_INVALID, "inconsistent component counts");
+    const bool enth = par->start_comp == par->rhoh_comp;
+    if (enth && par->do_eos_h_above_cutoff && !eos_mask)
+        return fail(MX_ERR_INVALID,
+                    "do_eos_h_above_cutoff: eos_mask is required (the EOS stays with the caller)");
+    MX_TRY(check_cover(geom, stateold, 0, -1, "stateold"));
+    MX_TRY(check_cover(geom, statenew, 0, -1, "statenew"));
+    MX_TRY(check_cover(geom, force, 0, -1, "force"));
+    MX_TRY(require_device());
+    Session S(stream);
+    const KGeom kg = make_kgeom(geom);
+    DFab so, sn, fo, fl[3];
+    const int c0 = enth ? par->rhoh_comp : par->first_spec;
+    const int nc = enth ? 1 : par->num_spec;
+    MX_TRY(S.fab(stateold, &so, c0, nc, true, false));
+    if (!enth) MX_TRY(S.upload(stateold, so, par->rho_comp, 1));
+    // statenew: the swept components are fully overwritten on valid zones only, so a host
+    // mirror must start from the caller's data (ghost zones survive the round trip)
+    MX_TRY(S.fab(statenew, &sn, c0, nc, true, true));
+    if (!enth) {
+        MX_TRY(S.upload(statenew, sn, par->rho_comp, 1));
+        MX_TRY(S.download_later(statenew, sn, par->rho_comp, 1));
+    } else {
+        MX_TRY(S.upload(statenew, sn, par->rho_comp, 1));  // read for the EOS flag
+    }
+    MX_TRY(S.fab(force, &fo, c0, nc, true, false));
+    for (int d = 0; d < geom->dim; ++d) {
+        MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
+        MX_TRY(S.fab(&sflux[d], &fl[d], c0, nc, true, false));
+    }
+    const size_t nzones = (size_t)(kg.vhi[0] - kg.vlo[0] + 1) * (kg.vhi[1] - kg.vlo[1] + 1) *
+                          (kg.dim == 3 ? kg.vhi[2] - kg.vlo[2] + 1 : 1);
+    unsigned char* dmask = eos_mask;
+    const bool host_mask = eos_mask && !is_device_ptr(eos_mask);
+    if (host_mask) {
+        void* p = nullptr;
+        CUDA_OK(S.alloc(&p, nzones));
+        dmask = static_cast<unsigned char*>(p);
+    }
+    void* dcount = nullptr;
+    CUDA_OK(S.alloc(&dcount, sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), S.stream()));
+    update_scal(kg, so, sn, fl, fo, *par, enth ? dmask : nullptr,
+                static_cast<unsigned long long*>(dcount), S.stream());
+    CUDA_OK(cudaGetLastError());
+    if (enth && host_mask)
+        CUDA_OK(cudaMemcpyAsync(eos_mask, dmask, nzones, cudaMemcpyDeviceToHost, S.stream()));
+    unsigned long long cnt = 0;
+    if (n_eos) {
+        CUDA_OK(cudaMemcpyAsync(&cnt, dcount, sizeof(cnt), cudaMemcpyDeviceToHost, S.stream()));
+        CUDA_OK(cudaStreamSynchronize(S.stream()));
+        *n_eos = (long long)cnt;
+    }
+    if (host_mask) CUDA_OK(cudaStreamSynchronize(S.stream()));
+    return S.finish();
 }
 
 long long mx_halo_count(const MxGeom* geom, const MxFab* fab, int dir, int ng, int ncomp) {

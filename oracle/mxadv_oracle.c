@@ -26,6 +26,7 @@
  *   Source/MaestroMakeFlux.cpp:18-465       -> orc_make_rhoX_flux()
  *   Source/MaestroMakeFlux.cpp:467-1067     -> orc_make_rhoh_flux()
  *   Source/MaestroCelltoEdge.cpp:5-55       -> orc_cell_to_edge()
+ *   Source/MaestroAdvection.cpp:86-251      -> orc_update_scal() (zone loop; EOS zones flagged)
  *   Source/MaestroMakew0.cpp:5-58,60-272    -> orc_make_w0_planar() (one radial level)
  *   Source/MaestroMakew0.cpp:537-740,942-969 + Source/MaestroMakeGrav.cpp:303-322
  *                                           -> orc_make_w0_sphr()
@@ -1185,5 +1186,99 @@ int orc_make_w0_sphr(const MxW0Params* p, const double* w0_old, const double* Sb
     }
     w0_force_cells(p, w0_old, w0, w0_force);
     free(buf);
+    return 0;
+}
+
+/* Maestro::UpdateScal, zone loop of one box: Source/MaestroAdvection.cpp:86-251.  The EOS call
+ * (:137-159, third-party Microphysics) is not restated: those zones are flagged in eos_mask. */
+static inline long fidx(const MxFab* f, int i, int j, int k) {
+    long nx = f->hi[0] - f->lo[0] + 1, ny = f->hi[1] - f->lo[1] + 1;
+    return (long)(i - f->lo[0]) + nx * ((long)(j - f->lo[1]) + ny * (long)(k - f->lo[2]));
+}
+static inline long fcomp(const MxFab* f) {
+    return (long)(f->hi[0] - f->lo[0] + 1) * (f->hi[1] - f->lo[1] + 1) * (f->hi[2] - f->lo[2] + 1);
+}
+
+int orc_update_scal(const MxGeom* g, const MxFab* sold, const MxFab* snew, const MxFab* sflux,
+                    const MxFab* force, const MxUpdateParams* p, unsigned char* eos_mask,
+                    long long* n_eos) {
+    const int dim = g->dim;
+    const int klo = dim == 3 ? g->valid_lo[2] : 0, khi = dim == 3 ? g->valid_hi[2] : 0;
+    const long so = fcomp(sold), sn = fcomp(snew), fo = fcomp(force);
+    const long fx = fcomp(&sflux[0]), fy = fcomp(&sflux[1]), fz = dim == 3 ? fcomp(&sflux[2]) : 0;
+    const double dt = p->dt;
+    const int nx = g->valid_hi[0] - g->valid_lo[0] + 1, ny = g->valid_hi[1] - g->valid_lo[1] + 1;
+    long long cnt = 0;
+    if (p->start_comp != p->rhoh_comp && p->start_comp != p->first_spec) return -1; /* :253 */
+    for (int k = klo; k <= khi; ++k)
+        for (int j = g->valid_lo[1]; j <= g->valid_hi[1]; ++j)
+            for (int i = g->valid_lo[0]; i <= g->valid_hi[0]; ++i) {
+                const long io = fidx(sold, i, j, k), in = fidx(snew, i, j, k);
+                const long ifo = fidx(force, i, j, k);
+                const long x0 = fidx(&sflux[0], i, j, k), x1 = fidx(&sflux[0], i + 1, j, k);
+                const long y0 = fidx(&sflux[1], i, j, k), y1 = fidx(&sflux[1], i, j + 1, k);
+                const long z0 = dim == 3 ? fidx(&sflux[2], i, j, k) : 0;
+                const long z1 = dim == 3 ? fidx(&sflux[2], i, j, k + 1) : 0;
+                if (p->start_comp == p->rhoh_comp) {
+                    const int c = p->rhoh_comp;
+                    double divterm = (sflux[0].p[c * fx + x1] - sflux[0].p[c * fx + x0]) / g->dx[0] +
+                                     (sflux[1].p[c * fy + y1] - sflux[1].p[c * fy + y0]) / g->dx[1];
+                    if (dim == 3)
+                        divterm = divterm +
+                                  (sflux[2].p[c * fz + z1] - sflux[2].p[c * fz + z0]) / g->dx[2];
+                    snew->p[c * sn + in] =
+                        sold->p[c * so + io] + dt * (-divterm + force->p[c * fo + ifo]);
+                    const int flag = p->do_eos_h_above_cutoff &&
+                                     snew->p[p->rho_comp * sn + in] <= p->base_cutoff_density;
+                    if (eos_mask) {
+                        eos_mask[(long)(i - g->valid_lo[0]) +
+                                 nx * ((long)(j - g->valid_lo[1]) + (long)ny * (k - klo))] =
+                            (unsigned char)flag;
+                    }
+                    cnt += flag;
+                    continue;
+                }
+                /* species, :161-183 */
+                for (int n = 0; n < p->num_spec; ++n) {
+                    const int c = p->first_spec + n;
+                    double divterm = (sflux[0].p[c * fx + x1] - sflux[0].p[c * fx + x0]) / g->dx[0];
+                    divterm += (sflux[1].p[c * fy + y1] - sflux[1].p[c * fy + y0]) / g->dx[1];
+                    if (dim == 3)
+                        divterm += (sflux[2].p[c * fz + z1] - sflux[2].p[c * fz + z0]) / g->dx[2];
+                    snew->p[c * sn + in] =
+                        sold->p[c * so + io] + dt * (-divterm + force->p[c * fo + ifo]);
+                }
+                /* density, floor, negative species, :186-251 */
+                double* rho = &snew->p[p->rho_comp * sn + in];
+                *rho = sold->p[p->rho_comp * so + io];
+                int has_negative_species = 0;
+                for (int c = p->start_comp; c < p->start_comp + p->num_spec; ++c) {
+                    *rho += snew->p[c * sn + in] - sold->p[c * so + io];
+                    if (snew->p[c * sn + in] < 0.0) has_negative_species = 1;
+                }
+                if (*rho < 0.5 * p->base_cutoff_density) {
+                    for (int c = p->start_comp; c < p->start_comp + p->num_spec; ++c)
+                        snew->p[c * sn + in] *= 0.5 * p->base_cutoff_density / *rho;
+                    *rho = 0.5 * p->base_cutoff_density;
+                }
+                if (has_negative_species) {
+                    for (int c = p->start_comp; c < p->start_comp + p->num_spec; ++c) {
+                        if (snew->p[c * sn + in] < 0.0) {
+                            double delta = -snew->p[c * sn + in];
+                            double sumX = 0.0;
+                            for (int c2 = p->start_comp; c2 < p->start_comp + p->num_spec; ++c2)
+                                if (c2 != c && snew->p[c2 * sn + in] >= 0.0)
+                                    sumX += snew->p[c2 * sn + in];
+                            for (int c2 = p->start_comp; c2 < p->start_comp + p->num_spec; ++c2)
+                                if (c2 != c && snew->p[c2 * sn + in] >= 0.0) {
+                                    double frac = snew->p[c2 * sn + in] / sumX;
+                                    snew->p[c2 * sn + in] -= frac * delta;
+                                }
+                            snew->p[c * sn + in] = 0.0;
+                        }
+                    }
+                }
+            }
+    if (n_eos) *n_eos = cnt;
     return 0;
 }

@@ -30,6 +30,7 @@ int maestro_verbose = 0;
 bool do_2d_planar_octant = false, do_planar_invsq_grav = false, add_pb = false;
 Real base_cutoff_density = -1.0, dpdt_factor = 0.0, planar_invsq_mass = 0.0,
      grav_const = -1.5e10;
+bool do_sponge = false, do_eos_h_above_cutoff = true;
 }  // namespace maestro
 int Rho = 0, RhoH = 1, Temp = 2, Pi = 3, FirstSpec = 4, NumSpec = 3, Nscal = 7;
 
@@ -372,6 +373,35 @@ int DRV(make_w0_sphr)(const MxW0Params* p, const double* w0_old, const double* S
                      const double* r_cc, const double* r_edge, double* w0, double* w0_force) {
     return run_w0(true, p, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, g1o, g1n, pmp,
                   etarho_cc, etarho_ec, r_cc, r_edge, w0, w0_force, nullptr);
+}
+
+// Maestro::UpdateScal, Source/MaestroAdvection.cpp:86 (one level, one box).  The reference
+// build applies its EOS (here the shim's stand-in, oracle/shim/Maestro.H) to the zones at or
+// below base_cutoff_density itself and reports nothing; the overlay build does the same
+// through mx_update_scal's eos_mask.
+int DRV(update_scal)(const MxGeom* g, const MxFab* sold, const MxFab* snew, const MxFab* sflux,
+                    const MxFab* force, const MxFab* p0_cart, const MxUpdateParams* p) {
+    Maestro m;
+    setup(m, g);
+    m.dt = p->dt;
+    maestro::base_cutoff_density = p->base_cutoff_density;
+    maestro::do_eos_h_above_cutoff = p->do_eos_h_above_cutoff != 0;
+    maestro::reflux_type = 1;
+    Rho = p->rho_comp;
+    RhoH = p->rhoh_comp;
+    Temp = p->temp_comp;
+    FirstSpec = p->first_spec;
+    NumSpec = p->num_spec;
+    Nscal = sold->ncomp;
+    Vector<MultiFab> so(1), sn(1), fo(1), p0(1);
+    alias(so[0], g, sold, -1);
+    alias(sn[0], g, snew, -1);
+    alias(fo[0], g, force, -1);
+    if (p0_cart) alias(p0[0], g, p0_cart, -1);
+    Vector<std::array<MultiFab, DIM>> sf;
+    alias_faces(sf, g, sflux);
+    m.UpdateScal(so, sn, sf, fo, p->start_comp, p->num_comp, p0);
+    return 0;
 }
 
 }  // extern "C"
