@@ -23,7 +23,7 @@ constexpr int stream4_smem_doubles() {
     return S4_NS * (32 + 2 * LA) * (16 + 2 * LA) + 9 * 512 + 32 + 16 * 512 + 5 * (ST_MAXZC + 2);
 }
 
-template <int PPM, bool BC, int MODE>
+template <int PPM, bool BC, int MODE, bool SPH>
 __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     constexpr int GX = 32, GY = 16;
     constexpr int LA = (PPM == 2) ? 3 : 2;  // stencil radius
@@ -95,7 +95,8 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     const long fx_sz = A.sflux[0].sz, fy_sz = A.sflux[1].sz, fz_sz = A.sflux[2].sz;
     const long eta_sz = A.eta.sz;
     const KFlux& F_ = A.f;
-    const bool sph = (MODE != 0) && F_.spherical;
+    constexpr bool sph = SPH;  // spherical flux forms (density pass only; compile-time so that
+                               // the planar instantiation carries no dead loads / registers)
     const bool lane31 = (tx == 31);
 
     // ---- base-state tables of this chunk (planes a0 .. k1) -------------------------------
@@ -626,7 +627,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
 #undef HS
 }
 
-template <int PPM, int MODE>
+template <int PPM, int MODE, bool SPH>
 __global__ void __launch_bounds__(512, 1) k_stream4(const __grid_constant__ FusedArgs A) {
     extern __shared__ double sm[];
     // physical-boundary code only in blocks whose (grown) tile reaches a domain face that has
@@ -642,32 +643,34 @@ __global__ void __launch_bounds__(512, 1) k_stream4(const __grid_constant__ Fuse
     if (A.bcdir[1]) bc |= (y0 - 1 <= g.dlo[1] + 2) || (y0 + BY >= g.dhi[1] - 2);
     if (A.bcdir[2]) bc |= (k0 - 1 <= g.dlo[2] + 2) || (k1 >= g.dhi[2] - 2);
     if (bc)
-        stream4_body<PPM, true, MODE>(A, sm);
+        stream4_body<PPM, true, MODE, SPH>(A, sm);
     else
-        stream4_body<PPM, false, MODE>(A, sm);
+        stream4_body<PPM, false, MODE, SPH>(A, sm);
 }
 
-template <int PPM, int MODE>
+template <int PPM, int MODE, bool SPH>
 int launch_stream4(const FusedArgs& A, cudaStream_t stream) {
     const size_t smem = sizeof(double) * (size_t)stream4_smem_doubles<PPM>();
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_stream4<PPM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_stream4<PPM, MODE, SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
         attr_set = true;
     }
     dim3 grid(A.ntx * A.nty, A.nzc);
-    k_stream4<PPM, MODE><<<grid, 512, smem, stream>>>(A);
+    k_stream4<PPM, MODE, SPH><<<grid, 512, smem, stream>>>(A);
     mx_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 template <int PPM>
 int launch_stream4_mode(const FusedArgs& A, cudaStream_t stream) {
-    if (A.mode == 0) return launch_stream4<PPM, 0>(A, stream);
-    if (A.mode == 1) return launch_stream4<PPM, 1>(A, stream);
-    return launch_stream4<PPM, 2>(A, stream);
+    if (A.mode == 0) return launch_stream4<PPM, 0, false>(A, stream);
+    if (A.mode == 1)
+        return A.f.spherical ? launch_stream4<PPM, 1, true>(A, stream)
+                             : launch_stream4<PPM, 1, false>(A, stream);
+    return launch_stream4<PPM, 2, false>(A, stream);
 }
 
 #endif

@@ -7,6 +7,6 @@ out=/root/repo/exp/$name
 mkdir -p $out
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 nvcc -O3 -std=c++17 -lineinfo -fmad=false $ARCH -Xcompiler -fPIC -Xptxas -v "$@" -c -o $out/mx_fused.o $src/mx_fused.cu 2> $out/mx_fused.ptxas.log
-nvcc $ARCH -shared -o $out/libmxadv.so $out/mx_fused.o $src/mx_api.o $src/mx_staged.o $src/mx_flux.o $src/mx_w0.o
+nvcc $ARCH -shared -o $out/libmxadv.so $out/mx_fused.o $(ls $src/*.o | grep -v mx_fused.o)
 rm -f $out/mx_fused.o
 echo built $out/libmxadv.so
