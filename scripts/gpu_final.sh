@@ -1,0 +1,14 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv
+nproc
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_512.json 2> gpurun_out/bench_512.err; tail -2 gpurun_out/bench_512.err; cat gpurun_out/bench_512.json
+python bench.py --size 256 > gpurun_out/bench_256.json 2> gpurun_out/bench_256.err; cat gpurun_out/bench_256.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cat gpurun_out/bench_ref.json
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 60 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --size 256 --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_stream4 -s 6 -c 2 -f -o gpurun_out/prof_r1c python bench.py --size 256 --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_stream4 -s 6 -c 2 --csv --log-file gpurun_out/traffic_512.csv python bench.py --size 512 --steps 1 --warmup 3 --no-cpu --no-e2e > /dev/null 2>&1
+grep -E "dram__|gpu__time" gpurun_out/traffic_512.csv | awk -F'","' '{print $5, $(NF-2), $(NF-1), $NF}' | cut -c1-140
