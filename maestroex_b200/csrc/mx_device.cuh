@@ -36,6 +36,18 @@ MXD double signed_mag(double mag, double sgn) {
 }
 MXD double sign1(double sgn) { return signed_mag(1.0, sgn); }
 
+// (prod > 0.0) ? r : +0.0 as a select.  Written in PTX because nvcc otherwise sinks the
+// computation of `r` under a divergent branch (BSSY / BRA / BSYNC per limiter: measured slower
+// than computing it unconditionally on every lane).
+MXD double sel_pos(double prod, double r) {
+    double out;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, 0d0000000000000000;\n\t"
+        "selp.f64 %0, %1, 0d0000000000000000, p;\n\t}"
+        : "=d"(out)
+        : "d"(r), "d"(prod));
+    return out;
+}
+
 // Correctly rounded x / c for the compile-time constants c = 6 and c = 3 (Markstein-style:
 // q0 = RN(x * RN(1/c)), r = x - c*q0 exactly via FMA, q = RN(q0 + r * RN(1/c))).  Verified
 // against IEEE division on 5.5e8 random and structured operands per divisor
@@ -60,7 +72,7 @@ MXD double div3(double x) {
 // ---------------------------------------------------------------------------------------
 MXD double mc_lim(double dpls, double dmn) {
     const double slim = dmin_(fabs(dpls), fabs(dmn));
-    return dpls * dmn > 0.0 ? slim : 0.0;
+    return sel_pos(dpls * dmn, slim);
 }
 
 MXD double slope2(const double* S, int I, int lo, int hi, bool lobc, bool hibc) {
@@ -176,7 +188,7 @@ MXD double vanleer(double sm1, double s0, double sp1) {
     const double dsr = 2.0 * (sp1 - s0);
     const double m = dmin_(fabs(dsc), dmin_(fabs(dsl), fabs(dsr)));
     const double r = signed_mag(m, dsc);
-    return (dsl * dsr > 0.0) ? r : 0.0;
+    return sel_pos(dsl * dsr, r);
 }
 
 // 4th-order edge between sL and sR with van Leer slopes dL, dR, clamped (MaestroPPM.cpp:62-67)
