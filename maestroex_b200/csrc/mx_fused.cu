@@ -586,6 +586,7 @@ int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
             return launch_stream5_mode<2>(A, stream);
         }
         if (!v3) {
+            A.nty = (ny + (S4_GY - 2) - 1) / (S4_GY - 2);
             if (ppm_type == 0) return launch_stream4_mode<0>(A, stream);
             if (ppm_type == 1) return launch_stream4_mode<1>(A, stream);
             return launch_stream4_mode<2>(A, stream);

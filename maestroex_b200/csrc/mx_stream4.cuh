@@ -16,16 +16,24 @@
 #define MX_STREAM4_CUH
 
 constexpr int S4_NS = 8;  // ring slots (power of two)
+// tile rows per block (incl. the one-cell halo) and resident blocks per SM
+#ifndef S4_GY
+#define S4_GY 16
+#endif
+#ifndef S4_MINB
+#define S4_MINB 1
+#endif
 
 template <int PPM>
 constexpr int stream4_smem_doubles() {
     constexpr int LA = (PPM == 2) ? 3 : 2;
-    return S4_NS * (32 + 2 * LA) * (16 + 2 * LA) + 9 * 512 + 32 + 16 * 512 + 5 * (ST_MAXZC + 2);
+    return S4_NS * (32 + 2 * LA) * (S4_GY + 2 * LA) + 9 * (32 * S4_GY) + 32 + 16 * (32 * S4_GY) +
+           5 * (ST_MAXZC + 2);
 }
 
 template <int PPM, bool BC, int MODE, bool SPH>
 __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
-    constexpr int GX = 32, GY = 16;
+    constexpr int GX = 32, GY = S4_GY;
     constexpr int LA = (PPM == 2) ? 3 : 2;  // stencil radius
     constexpr int PW = GX + 2 * LA, PH = GY + 2 * LA;
     constexpr int PL = PW * PH;  // doubles per ring plane
@@ -628,11 +636,11 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
 }
 
 template <int PPM, int MODE, bool SPH>
-__global__ void __launch_bounds__(512, 1) k_stream4(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(32 * S4_GY, S4_MINB) k_stream4(const __grid_constant__ FusedArgs A) {
     extern __shared__ double sm[];
     // physical-boundary code only in blocks whose (grown) tile reaches a domain face that has
     // a non-interior BC; everything else runs the BC-free instantiation
-    constexpr int BX = 30, BY = 14;
+    constexpr int BX = 30, BY = S4_GY - 2;
     const KGeom& g = A.g;
     const int bx = blockIdx.x % A.ntx, by = blockIdx.x / A.ntx;
     const int x0 = g.vlo[0] + bx * BX, y0 = g.vlo[1] + by * BY;
@@ -659,7 +667,7 @@ int launch_stream4(const FusedArgs& A, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid(A.ntx * A.nty, A.nzc);
-    k_stream4<PPM, MODE, SPH><<<grid, 512, smem, stream>>>(A);
+    k_stream4<PPM, MODE, SPH><<<grid, 32 * S4_GY, smem, stream>>>(A);
     mx_count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
