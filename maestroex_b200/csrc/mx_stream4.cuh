@@ -312,8 +312,11 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             const bool px_pos = um > 0.0, px_nz0 = fabs(um) > 0.0, px_nz = fabs(um) > eps;
             const bool py_pos = vm > 0.0, py_nz0 = fabs(vm) > 0.0, py_nz = fabs(vm) > eps;
             const bool pz_pos = w_0 > 0.0, pz_nz0 = fabs(w_0) > 0.0, pz_nz = fabs(w_0) > eps;
+            // high y face (its first Riemann solve is formed here too, see P2)
+            const bool py2_pos = vp > 0.0, py2_nz0 = fabs(vp) > 0.0;
             const bool slow_c = __any_sync(
-                0xffffffffu, !(px_nz0 && px_nz && py_nz0 && py_nz && pz_nz0 && pz_nz));
+                0xffffffffu,
+                !(px_nz0 && px_nz && py_nz0 && py_nz && pz_nz0 && pz_nz && py2_nz0));
             const bool slow = slow_c || slow_p;
 
             // ---- P1: x / y reconstruction of plane a ------------------------------------
@@ -359,6 +362,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                 }
             }
             X_IPY[tid] = ipy;
+            if (PPM != 0) X_SY[tid] = imy;  // right state of my low y face, for the row below
             cp_async_wait<1>();  // this thread's share of plane a+LA has landed
             __syncthreads();     // S2: publishes IPY and ring plane a+LA
 
@@ -430,13 +434,28 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             const double shx = upw(px_pos, px_nz0, slow, slx, srx);  // QUIRK: |u| > 0.0 (:746)
             const double shy = upw(py_pos, py_nz0, slow, sly, sry);
             const double shz = upw(pz_pos, pz_nz0, slow, slz, srz);
-            X_SY[tid] = shy;
-            __syncthreads();  // S3
+            // first Riemann solve of my HIGH y face (the row above's low face), formed here from
+            // my own left state and the neighbour's right state published at S2: saves the
+            // exchange round (barrier S3) that passing its result down would cost
+            double shy_up;
+            {
+                double l, r;
+                if (PPM == 0) {
+                    const double qy = div_h<1>(A, dt * vp);
+                    l = s0 + 0.5 * (1.0 - qy) * ipy;
+                    r = pa[PW] - 0.5 * (1.0 + qy) * X_IPY[tid + GX];
+                } else {
+                    l = ipy;
+                    r = X_SY[tid + GX];
+                }
+                if (BC) bc_pair(j + 1, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, l, r);
+                shy_up = upw(py2_pos, py2_nz0, slow, l, r);
+            }
 
             // ---- P3: transverse differences (dt/6 form) ---------------------------------
             const double usx = up + um, usy = vp + vm;
             const double t6x = (c6x * usx) * (shfl_dn1(shx) - shx);
-            const double t6y = (c6y * usy) * (X_SY[tid + GX] - shy);
+            const double t6y = (c6y * usy) * (shy_up - shy);
             const double wsum_p = w_0 + w_m1;  // faces a and a-1: cell a-1
             const double tz = (c6z * wsum_p) * (shz - HS(H_SHZ));
             HS(H_SHZ) = shz;
@@ -510,22 +529,25 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             HS(H_T6Y) = t6y;
             X_HYX[tid] = hyx;
             X_HYZ[tid] = hyz;
-            __syncthreads();  // S5
-
-            // ---- P5: transverse differences (dt/4 form) ---------------------------------
-            const double c4xu = c4x * usx, c4yu = c4y * usy, c4zw = c4z * wsum_p;
-            const double t4xy = c4xu * (shfl_dn1(hxy) - hxy);
-            const double t4yx = c4yu * (X_HYX[tid + GX] - hyx);
-            const double t4yz = HS(H_C4Y) * (X_HYZ[tid + GX] - hyz);
-            const double t4zy = c4zw * (hzy - HS(H_HZY));
+            // the dt/4 terms the row above needs for its low y face do not depend on this
+            // exchange round (x shuffle / own z history only): publish them with it, which
+            // makes a separate round (barrier S6) unnecessary
+            const double c4zw = c4z * wsum_p;
             const double t4xz = HS(H_C4X) * (shfl_dn1(hxz) - hxz);
             const double t4zx = c4zw * (hzx - HS(H_HZX));
-            const double fs_cur = A.dt2 * f0;
             const double fs_prev = HS(H_FS);
             X_QY1[tid] = t4xz;
             X_QY2[tid] = t4zx;
             X_FS[tid] = fs_prev;
-            __syncthreads();  // S6
+            __syncthreads();  // S5
+
+            // ---- P5: transverse differences (dt/4 form) ---------------------------------
+            const double c4xu = c4x * usx, c4yu = c4y * usy;
+            const double t4xy = c4xu * (shfl_dn1(hxy) - hxy);
+            const double t4yx = c4yu * (X_HYX[tid + GX] - hyx);
+            const double t4yz = HS(H_C4Y) * (X_HYZ[tid + GX] - hyz);
+            const double t4zy = c4zw * (hzy - HS(H_HZY));
+            const double fs_cur = A.dt2 * f0;
 
             // ---- P6: final edge states (+ fluxes) ---------------------------------------
             if (do_xy) {  // block uniform: x / y faces of plane p = a-1
