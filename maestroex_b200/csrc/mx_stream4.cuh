@@ -27,7 +27,7 @@ constexpr int S4_NS = 8;  // ring slots (power of two)
 template <int PPM>
 constexpr int stream4_smem_doubles() {
     constexpr int LA = (PPM == 2) ? 3 : 2;
-    return S4_NS * (32 + 2 * LA) * (S4_GY + 2 * LA) + 9 * (32 * S4_GY) + 32 + 16 * (32 * S4_GY) +
+    return S4_NS * (32 + 2 * LA) * (S4_GY + 2 * LA) + 9 * (32 * S4_GY + 64) + 16 * (32 * S4_GY) +
            5 * (ST_MAXZC + 2);
 }
 
@@ -42,17 +42,21 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     constexpr int NLD = (PL + NT - 1) / NT;
 
     double* ring = smem;
-    double* ex = ring + S4_NS * PL;  // y-neighbour exchange arrays
-    double* X_IPY = ex + 0 * NT;
-    double* X_SY = ex + 1 * NT;
-    double* X_T6X = ex + 2 * NT;
-    double* X_TZ = ex + 3 * NT;
-    double* X_HYX = ex + 4 * NT;
-    double* X_HYZ = ex + 5 * NT;
-    double* X_QY1 = ex + 6 * NT;
-    double* X_QY2 = ex + 7 * NT;
-    double* X_FS = ex + 8 * NT;
-    double* hist = ex + 9 * NT + GX;  // thread-private z history (slot v of thread tid)
+    // y-neighbour exchange arrays, each with one row of never-written slack on either side: the
+    // outermost tile rows read "their neighbour" there (their y-direction results are never
+    // stored), so no thread ever reads a slot another thread writes without a barrier between
+    constexpr int XS = NT + 2 * GX;
+    double* ex = ring + S4_NS * PL + GX;
+    double* X_IPY = ex + 0 * XS;
+    double* X_SY = ex + 1 * XS;
+    double* X_T6X = ex + 2 * XS;
+    double* X_TZ = ex + 3 * XS;
+    double* X_HYX = ex + 4 * XS;
+    double* X_HYZ = ex + 5 * XS;
+    double* X_QY1 = ex + 6 * XS;
+    double* X_QY2 = ex + 7 * XS;
+    double* X_FS = ex + 8 * XS;
+    double* hist = ex + 9 * XS - GX;  // thread-private z history (slot v of thread tid)
     double* tab = hist + 16 * NT;     // per-plane base-state values of this chunk
     double* T_RXY = tab;              // 0.5 (rho0_old + rho0_new)(p)          x/y faces
     double* T_RZ = tab + (ST_MAXZC + 2);       // 0.5 (rho0_edge_old + _new)(a) z faces
