@@ -22,7 +22,12 @@
 // the reference's tile box ("index-space extents"): everything is
 // recomputed on the tile's one-cell halo instead of being exchanged between blocks.
 #include <algorithm>
+#include <array>
 #include <cmath>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <vector>
 #include <cstdlib>
 #include <cstring>
 
@@ -555,7 +560,42 @@ bool stream_ok(const FusedArgs& A) {
     return ok;
 }
 
-// chunking of the z range (see chunk_range): short boundary chunks only for k_stream4/5
+// chunking of the z range (see chunk_range): short boundary chunks only for k_stream4/5.
+// Unless MXADV_ZCHUNK fixes it, the chunk length is chosen by simulating the block schedule
+// (one resident block per SM): long chunks amortise the 2.5 planes of per-chunk overhead
+// (512^3: 118.7 ms at 63 planes vs 123.0 at 32), short ones balance the last wave (256^3: 15.5 ms
+// at 43 vs 16.8 at 32); profiles/r1c_experiments.md.
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// makespan (in plane-iterations) of `tiles` x chunks blocks handed out in launch order
+// (blockIdx.x fastest) to `sms` SMs, one resident block each; a chunk of len planes costs
+// len + 2.5 (two extra planes + prologue, fitted to the 512^3 z-chunk scan)
+double chunk_makespan(long tiles, int sms, const std::vector<int>& lens) {
+    std::vector<double> free_at(sms, 0.0);
+    std::make_heap(free_at.begin(), free_at.end(), std::greater<double>());
+    double end = 0.0;
+    for (int len : lens) {
+        const double d = len + 2.5;
+        for (long t = 0; t < tiles; ++t) {
+            std::pop_heap(free_at.begin(), free_at.end(), std::greater<double>());
+            const double f = free_at.back() + d;
+            free_at.back() = f;
+            end = f > end ? f : end;
+            std::push_heap(free_at.begin(), free_at.end(), std::greater<double>());
+        }
+    }
+    return end;
+}
+
 void set_zchunks(FusedArgs& A, bool allow_short) {
     const int nz = A.g.vhi[2] - A.g.vlo[2] + 1;
     A.zs_lo = A.zs_hi = 0;
@@ -564,7 +604,38 @@ void set_zchunks(FusedArgs& A, bool allow_short) {
         if (A.g.vhi[2] >= A.g.dhi[2] - 3) A.zs_hi = 4;
     }
     const int mid = nz - A.zs_lo - A.zs_hi;
-    A.nzc = (mid + A.zc - 1) / A.zc + (A.zs_lo ? 1 : 0) + (A.zs_hi ? 1 : 0);
+    const int nshort = (A.zs_lo ? 1 : 0) + (A.zs_hi ? 1 : 0);
+    if (allow_short && !getenv("MXADV_ZCHUNK") && mid > 24) {
+        // pick the chunk length with the smallest simulated makespan; cached per shape
+        const long tiles = (long)A.ntx * A.nty;
+        static std::map<std::array<long, 4>, int> cache;
+        static std::mutex mtx;
+        const std::array<long, 4> key = {tiles, mid, A.zs_lo, A.zs_hi};
+        std::lock_guard<std::mutex> lock(mtx);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            const int sms = sm_count();
+            double best = -1.0;
+            int best_zc = A.zc;
+            for (int n = (mid + ST_MAXZC - 3) / (ST_MAXZC - 2); n <= (mid + 23) / 24; ++n) {
+                const int zc = (mid + n - 1) / n;
+                if (zc > ST_MAXZC - 2) continue;
+                std::vector<int> lens;
+                if (A.zs_lo) lens.push_back(A.zs_lo);
+                for (int c = 0, left = mid; c < n && left > 0; ++c, left -= zc)
+                    lens.push_back(left < zc ? left : zc);
+                if (A.zs_hi) lens.push_back(A.zs_hi);
+                const double m = chunk_makespan(tiles, sms, lens);
+                if (best < 0.0 || m < best) {
+                    best = m;
+                    best_zc = zc;
+                }
+            }
+            it = cache.emplace(key, best_zc).first;
+        }
+        A.zc = it->second;
+    }
+    A.nzc = (mid + A.zc - 1) / A.zc + nshort;
 }
 
 int dispatch(FusedArgs& A, int ppm_type, bool bc, cudaStream_t stream) {
