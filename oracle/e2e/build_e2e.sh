@@ -1,0 +1,77 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE (not product code): builds the whole-code parity check of north_star —
+# "the fcompare diff of plotfiles after 10 full time steps must stay within 1e-10".
+#
+# Two executables of the reference problem Exec/test_problems/reacting_bubble are built with the
+# reference's own GNU-make system, CPU build (USE_MPI=FALSE USE_OMP=TRUE COMP=gnu), from the
+# sources where they lie under /root/reference (the problem directory is copied to a scratch
+# path because the reference tree is read-only and make writes tmp_build_dir/ into the cwd):
+#   Maestro<D>d.ref.ex  the UNMODIFIED reference
+#   Maestro<D>d.mx.ex   the same build with maestroex_b200/overlay/ shadowing
+#                       MaestroMakeEdgeScalars.cpp, MaestroMakeFlux.cpp, MaestroCelltoEdge.cpp,
+#                       MaestroMakew0.cpp and Maestro::UpdateScal, linked against libmxadv.so
+#                       exactly as INTEGRATION.md section 1 / 2b tells a maintainer to
+# plus AMReX's fcompare (external/amrex/Tools/Plotfile).  Outputs go only to oracle/_ref/e2e/
+# (git-ignored; travels to the GPU box, where /root/reference does not exist).  Nothing is
+# copied from the reference into the repository history.
+#
+# usage: oracle/e2e/build_e2e.sh [2|3]        (default 2)
+set -euo pipefail
+DIM=${1:-2}
+REF=${MAESTROEX_REF:-/root/reference}
+REPO=$(cd "$(dirname "$0")/../.." && pwd)
+OUT=$REPO/oracle/_ref/e2e
+WORK=${E2E_WORK:-/tmp/e2e}
+J=${E2E_JOBS:-$(nproc)}
+MK="make -j$J MAESTROEX_HOME=$REF DIM=$DIM USE_MPI=FALSE USE_OMP=TRUE COMP=gnu"
+mkdir -p "$OUT" "$WORK"
+
+# 1. the unmodified reference
+if [ ! -d "$WORK/rb_ref$DIM" ]; then
+    cp -r "$REF/Exec/test_problems/reacting_bubble" "$WORK/rb_ref$DIM"
+fi
+(cd "$WORK/rb_ref$DIM" && $MK > build.log 2>&1)
+cp "$WORK/rb_ref$DIM/Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.ref.ex"
+
+# 2. the overlay build: start from the reference's object files, drop the shadowed ones
+make -C "$REPO/maestroex_b200/csrc" > /dev/null
+rm -rf "$WORK/rb_mx$DIM"
+cp -r "$WORK/rb_ref$DIM" "$WORK/rb_mx$DIM"
+cd "$WORK/rb_mx$DIM"
+rm -f Maestro${DIM}d.gnu.OMP.ex
+for f in MaestroMakeEdgeScalars MaestroMakeFlux MaestroCelltoEdge MaestroMakew0 MaestroAdvection; do
+    find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
+done
+python3 - "$REPO" <<'EOF'
+import sys
+repo = sys.argv[1]
+mk = open("GNUmakefile").read()
+inc = "include $(MAESTROEX_HOME)/Exec/Make.Maestro"
+add = f"""MXADV_HOME := {repo}
+Bpack   += $(MXADV_HOME)/maestroex_b200/overlay/Make.package
+Blocs   += $(MXADV_HOME)/maestroex_b200/overlay $(MXADV_HOME)/include
+LIBRARIES         += -lmxadv
+LIBRARY_LOCATIONS += $(MXADV_HOME)/maestroex_b200/csrc
+CEXE_sources += MaestroUpdateScal.cpp
+"""
+tail = """
+$(objEXETempDir)/MaestroAdvection.o: CPPFLAGS += -DUpdateScal=UpdateScal_reference
+"""
+assert inc in mk
+open("GNUmakefile", "w").write(mk.replace(inc, add + inc + tail))
+EOF
+$MK > build_mx.log 2>&1
+cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.mx.ex"
+
+# 3. fcompare
+if [ ! -d "$WORK/plotfile" ]; then cp -r "$REF/external/amrex/Tools/Plotfile" "$WORK/plotfile"; fi
+(cd "$WORK/plotfile" && make -j$J AMREX_HOME=$REF/external/amrex DIM=$DIM USE_MPI=FALSE COMP=gnu \
+    programs=fcompare > build.log 2>&1)
+cp "$WORK/plotfile/fcompare.gnu.ex" "$OUT/fcompare${DIM}d.ex"
+
+# 4. run-time data of the problem (inputs, initial model, EOS table; the table is 60 MB of
+#    text, shipped gzipped)
+cp "$WORK/rb_ref$DIM"/inputs_${DIM}d_C "$WORK/rb_ref$DIM"/model.hse.cool.coulomb "$OUT/"
+[ -f "$OUT/helm_table.dat.gz" ] || gzip -c "$REF/external/Microphysics/EOS/helmholtz/helm_table.dat" > "$OUT/helm_table.dat.gz"
+strip "$OUT"/*.ex
+ls -la "$OUT"

@@ -1,0 +1,92 @@
+"""north_star's whole-code criterion: "the fcompare diff of plotfiles after 10 full time steps
+must stay within 1e-10".
+
+oracle/e2e/build_e2e.sh builds (in the authoring container, where /root/reference exists) the
+UNMODIFIED reference problem Exec/test_problems/reacting_bubble and the same problem with
+maestroex_b200/overlay/ shadowing MaestroMakeEdgeScalars.cpp / MaestroMakeFlux.cpp /
+MaestroCelltoEdge.cpp / MaestroMakew0.cpp / Maestro::UpdateScal on libmxadv.so, both with the
+reference's own GNU-make system (CPU AMReX, OpenMP), plus AMReX's fcompare.  Here both run
+`inputs_<D>d_C` for 10 steps (single level; 15 boxes of 64^2 in 2-D, 64 boxes of 32^3 in 3-D; burner, projections, EOS
+are the reference's own code in both) and the step-10 plotfiles are compared variable by
+variable.  The executables hold host MultiFabs, so every overlay call goes through the C ABI's
+host-fab staging path onto the GPU.  Nothing here reads /root/reference at run time."""
+import gzip
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+E2E = os.path.join(ROOT, "oracle", "_ref", "e2e")
+CSRC = os.path.join(ROOT, "maestroex_b200", "csrc")
+FCOMPARE_TOL = 1e-10  # north_star
+NSTEPS = 10
+
+
+def _table(tmp):
+    dst = os.path.join(tmp, "helm_table.dat")
+    with gzip.open(os.path.join(E2E, "helm_table.dat.gz"), "rb") as f, open(dst, "wb") as g:
+        shutil.copyfileobj(f, g, 1 << 24)
+    return dst
+
+
+def _run(exe, rundir, dim, table, extra=()):
+    os.makedirs(rundir)
+    for f in (f"inputs_{dim}d_C", "model.hse.cool.coulomb"):
+        shutil.copy(os.path.join(E2E, f), rundir)
+    os.symlink(table, os.path.join(rundir, "helm_table.dat"))
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = CSRC + ":" + env.get("LD_LIBRARY_PATH", "")
+    env.setdefault("OMP_NUM_THREADS", str(min(16, os.cpu_count() or 1)))
+    cmd = [os.path.join(E2E, exe), f"inputs_{dim}d_C", f"maestro.max_step={NSTEPS}",
+           f"maestro.plot_int={NSTEPS}", "maestro.chk_int=-1", "maestro.plot_deltat=-1",
+           *extra]
+    r = subprocess.run(cmd, cwd=rundir, env=env, capture_output=True, text=True, timeout=1500)
+    open(os.path.join(rundir, "run.log"), "w").write(r.stdout + r.stderr)
+    assert r.returncode == 0, (exe, r.stdout[-2000:], r.stderr[-2000:])
+    plt = os.path.join(rundir, "plt%07d" % NSTEPS)
+    assert os.path.isdir(plt), os.listdir(rundir)
+    return plt, r.stdout
+
+
+def parse_fcompare(text):
+    """{variable: (abs_err, rel_err)} from fcompare's table (Tools/Plotfile/fcompare.cpp)"""
+    out = {}
+    for line in text.splitlines():
+        m = re.match(r"^\s(\S.*?)\s+([-+0-9.eE]+|nan|inf)\s+([-+0-9.eE]+|nan|inf)\s*$", line)
+        if m and not m.group(1).startswith("variable"):
+            out[m.group(1).strip()] = (float(m.group(2)), float(m.group(3)))
+    return out
+
+
+@pytest.mark.parametrize("dim,extra", [
+    (2, ()),                                   # inputs_2d_C as shipped: ppm_type 0
+    (2, ("maestro.ppm_type=1",)),
+    (2, ("maestro.ppm_type=2",)),
+    (3, ()),                                   # inputs_3d_C as shipped: 64x64x512, ppm_type 1
+])
+def test_fcompare_10_steps(tmp_path, dim, extra):
+    for f in (f"Maestro{dim}d.ref.ex", f"Maestro{dim}d.mx.ex", f"fcompare{dim}d.ex",
+              "helm_table.dat.gz"):
+        if not os.path.exists(os.path.join(E2E, f)):
+            pytest.skip(f"oracle/_ref/e2e/{f} not built (oracle/e2e/build_e2e.sh {dim})")
+    tmp = str(tmp_path)
+    table = _table(tmp)
+    pr, _ = _run(f"Maestro{dim}d.ref.ex", os.path.join(tmp, "ref"), dim, table, extra)
+    pm, _ = _run(f"Maestro{dim}d.mx.ex", os.path.join(tmp, "mx"), dim, table, extra)
+    r = subprocess.run([os.path.join(E2E, f"fcompare{dim}d.ex"), "-a", pr, pm],
+                       capture_output=True, text=True, timeout=600)
+    table_txt = r.stdout
+    keep = os.environ.get("MXADV_FCOMPARE_OUT")
+    if keep:
+        os.makedirs(keep, exist_ok=True)
+        tag = f"{dim}d" + "".join("_" + e.split(".")[-1].replace(" ", "x") for e in extra)
+        open(os.path.join(keep, f"fcompare_{tag}.txt"), "w").write(table_txt + r.stderr)
+    errs = parse_fcompare(table_txt)
+    assert len(errs) >= 20, table_txt[-3000:]
+    worst = max(errs.items(), key=lambda kv: kv[1][1])
+    assert worst[1][1] <= FCOMPARE_TOL, (worst, table_txt[-3000:])
