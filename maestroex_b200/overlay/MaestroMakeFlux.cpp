@@ -74,15 +74,17 @@ void Maestro::MakeRhoXFlux(
             if (flux_reg_s[lev + 1]) {
                 for (int i = 0; i < AMREX_SPACEDIM; ++i) {
                     flux_reg_s[lev + 1]->CrseInit(sflux[lev][i], i, start_comp, start_comp,
-                                                  num_comp, -1.0 * dt);
-                    flux_reg_s[lev + 1]->CrseInit(sflux[lev][i], i, Rho, Rho, 1, -1.0 * dt);
+                                                  num_comp, -1.0 * dt * mxadv::face_area(geom[lev], i));
+                    flux_reg_s[lev + 1]->CrseInit(sflux[lev][i], i, Rho, Rho, 1,
+                                                  -1.0 * dt * mxadv::face_area(geom[lev], i));
                 }
             }
             if (flux_reg_s[lev]) {
                 for (int i = 0; i < AMREX_SPACEDIM; ++i) {
                     flux_reg_s[lev]->FineAdd(sflux[lev][i], i, start_comp, start_comp,
-                                             num_comp, 1.0 * dt);
-                    flux_reg_s[lev]->FineAdd(sflux[lev][i], i, Rho, Rho, 1, 1.0 * dt);
+                                             num_comp, 1.0 * dt * mxadv::face_area(geom[lev], i));
+                    flux_reg_s[lev]->FineAdd(sflux[lev][i], i, Rho, Rho, 1,
+                                             1.0 * dt * mxadv::face_area(geom[lev], i));
                 }
             }
         }
@@ -145,12 +147,14 @@ void Maestro::MakeRhoHFlux(
         for (int lev = 0; lev <= finest_level; ++lev) {
             if (flux_reg_s[lev + 1]) {
                 for (int i = 0; i < AMREX_SPACEDIM; ++i) {
-                    flux_reg_s[lev + 1]->CrseInit(sflux[lev][i], i, RhoH, RhoH, 1, -1.0 * dt);
+                    flux_reg_s[lev + 1]->CrseInit(sflux[lev][i], i, RhoH, RhoH, 1,
+                                                  -1.0 * dt * mxadv::face_area(geom[lev], i));
                 }
             }
             if (flux_reg_s[lev]) {
                 for (int i = 0; i < AMREX_SPACEDIM; ++i) {
-                    flux_reg_s[lev]->FineAdd(sflux[lev][i], i, RhoH, RhoH, 1, 1.0 * dt);
+                    flux_reg_s[lev]->FineAdd(sflux[lev][i], i, RhoH, RhoH, 1,
+                                             1.0 * dt * mxadv::face_area(geom[lev], i));
                 }
             }
         }

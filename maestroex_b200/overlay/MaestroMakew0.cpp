@@ -92,6 +92,9 @@ void Maestro::Makew0Planar(const BaseState<Real>& w0_old, BaseState<Real>& w0_fo
                                    row0(etarho_cc), row0(w0), row0(w0_force), &pb,
                                    mxadv::stream()),
                  "Makew0Planar");
+#ifdef AMREX_USE_CUDA
+    Gpu::streamSynchronize();  // w0 / w0_force (managed memory) are read on the host next
+#endif
     if (add_pb) {  // :175-180
         p0bdot = pb;
         p0b = p0bdot * dt;
@@ -117,6 +120,9 @@ void Maestro::Makew0Sphr(const BaseState<Real>& w0_old, BaseState<Real>& w0_forc
                                  base_geom.r_cc_loc.dataPtr(), base_geom.r_edge_loc.dataPtr(),
                                  row0(w0), row0(w0_force), mxadv::stream()),
                  "Makew0Sphr");
+#ifdef AMREX_USE_CUDA
+    Gpu::streamSynchronize();  // w0 / w0_force (managed memory) are read on the host next
+#endif
 }
 
 void Maestro::Makew0PlanarVarg(const BaseState<Real>&, BaseState<Real>&, const BaseState<Real>&,

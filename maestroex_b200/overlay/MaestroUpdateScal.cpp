@@ -39,6 +39,40 @@ void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& sta
             const MxFab fo = mxadv::fab_of(force[lev].const_array(mfi));
             const mxadv::Faces sf = mxadv::faces_of(sflux[lev], mfi);
             const bool enth = start_comp == RhoH;
+#ifdef AMREX_USE_GPU
+            // GPU AMReX: fabs are device memory.  The zone flags stay on the device and the
+            // reference's own eos() runs there, on the flagged zones, in AMReX's stream
+            // (same statements as :137-159)
+            Gpu::DeviceVector<unsigned char> dmask;
+            if (enth && do_eos_h_above_cutoff) dmask.resize(vbx.numPts());
+            mxadv::check(mx_update_scal(&g, &so, &sn, sf.f, &fo, &par,
+                                        dmask.empty() ? nullptr : dmask.data(), nullptr,
+                                        mxadv::stream()),
+                         "UpdateScal");
+            if (!dmask.empty()) {
+                const Array4<const Real> sold_arr = stateold[lev].const_array(mfi);
+                const Array4<Real> snew_arr = statenew[lev].array(mfi);
+                const Array4<const Real> p0_arr = p0_cart[lev].const_array(mfi);
+                const unsigned char* AMREX_RESTRICT mk = dmask.data();
+                const Dim3 vlo = amrex::lbound(vbx);
+                const Dim3 vln = amrex::length(vbx);
+                ParallelFor(vbx, [=] AMREX_GPU_DEVICE(int i, int j, int k) {
+                    const long q = (long)(i - vlo.x) +
+                                   (long)vln.x * ((long)(j - vlo.y) + (long)vln.y * (k - vlo.z));
+                    if (!mk[q]) return;
+                    eos_rh_t eos_state;
+                    eos_state.rho = snew_arr(i, j, k, Rho);
+                    eos_state.T = sold_arr(i, j, k, Temp);
+                    eos_state.p = p0_arr(i, j, k);
+                    for (auto n = 0; n < NumSpec; ++n) {
+                        eos_state.xn[n] = snew_arr(i, j, k, FirstSpec + n) / eos_state.rho;
+                    }
+                    eos(eos_input_rp, eos_state);
+                    snew_arr(i, j, k, RhoH) = snew_arr(i, j, k, Rho) * eos_state.h;
+                });
+                Gpu::streamSynchronize();  // dmask is freed at the end of this iteration
+            }
+#else
             std::vector<unsigned char> mask;
             long long n_eos = 0;
             if (enth && do_eos_h_above_cutoff) mask.assign(vbx.numPts(), 0);
@@ -74,6 +108,7 @@ void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& sta
                     }
                 }
             }
+#endif
         }
     }
 

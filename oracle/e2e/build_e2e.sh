@@ -63,6 +63,31 @@ EOF
 $MK > build_mx.log 2>&1
 cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.mx.ex"
 
+# 2b. (3-D) the fused overlay on top: DensityAdvance / EnthalpyAdvance shadowed as well, so the
+#     run goes through mx_density_edge_flux / mx_enthalpy_edge_flux, the kernels bench.py times
+if [ "$DIM" = 3 ]; then
+    rm -rf "$WORK/rb_fx$DIM"
+    cp -r "$WORK/rb_mx$DIM" "$WORK/rb_fx$DIM"
+    cd "$WORK/rb_fx$DIM"
+    rm -f Maestro${DIM}d.gnu.OMP.ex
+    for f in MaestroDensityAdvance MaestroEnthalpyAdvance; do
+        find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
+    done
+    python3 - "$REPO" <<'EOF2'
+import sys
+repo = sys.argv[1]
+mk = open("GNUmakefile").read()
+key = "LIBRARIES         += -lmxadv"
+add = """Bpack   += $(MXADV_HOME)/maestroex_b200/overlay_fused/Make.package
+Blocs   += $(MXADV_HOME)/maestroex_b200/overlay_fused
+"""
+assert key in mk
+open("GNUmakefile", "w").write(mk.replace(key, add + key))
+EOF2
+    $MK > build_fx.log 2>&1
+    cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.fx.ex"
+fi
+
 # 3. fcompare
 if [ ! -d "$WORK/plotfile" ]; then cp -r "$REF/external/amrex/Tools/Plotfile" "$WORK/plotfile"; fi
 (cd "$WORK/plotfile" && make -j$J AMREX_HOME=$REF/external/amrex DIM=$DIM USE_MPI=FALSE COMP=gnu \

@@ -1,0 +1,67 @@
+#!/bin/bash
+# MEASUREMENT SCRIPT for the GPU box (reads nothing under /root/reference).  Runs the two CUDA
+# executables built by build_e2e_cuda.sh — the unmodified reference and the overlay build on
+# libmxadv.so — on the same B200 for NSTEPS steps of reacting_bubble inputs_3d_C, then
+#   * fcompare of the two step-NSTEPS plotfiles, and
+#   * the TinyProfiler inclusive times of the hot-path members in both runs
+#     (tiny_profiler.device_synchronize_around_region=1, so a region's time is the device time
+#     of the work it launched).
+# usage: run_cuda_compare.sh OUTDIR TAG [extra ParmParse arguments...]
+set -uo pipefail
+OUTDIR=$1; TAG=$2; shift 2
+REPO=$(cd "$(dirname "$0")/../.." && pwd)
+E2E=$REPO/oracle/_ref/e2e
+NSTEPS=${NSTEPS:-10}
+NVTXDIR=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nvtx/lib
+export LD_LIBRARY_PATH=$REPO/maestroex_b200/csrc:$NVTXDIR:${LD_LIBRARY_PATH:-}
+mkdir -p "$OUTDIR"
+OUTDIR=$(cd "$OUTDIR" && pwd)
+TMP=$(mktemp -d)
+gunzip -c "$E2E/helm_table.dat.gz" > "$TMP/helm_table.dat"
+for arm in ref mx; do
+    mkdir -p "$TMP/$arm"
+    cp "$E2E/inputs_3d_C" "$E2E/model.hse.cool.coulomb" "$TMP/$arm/"
+    ln -s "$TMP/helm_table.dat" "$TMP/$arm/helm_table.dat"
+    (cd "$TMP/$arm" && timeout 900 "$E2E/Maestro3d.cuda.$arm.ex" inputs_3d_C \
+        maestro.max_step=$NSTEPS maestro.plot_int=$NSTEPS maestro.chk_int=-1 maestro.plot_deltat=-1 \
+        tiny_profiler.device_synchronize_around_region=1 amrex.fpe_trap_invalid=0 "$@" \
+        > "$OUTDIR/run_${TAG}_$arm.log" 2>&1; echo "rc=$?" >> "$OUTDIR/run_${TAG}_$arm.log")
+    tail -1 "$OUTDIR/run_${TAG}_$arm.log"
+done
+PLT=$(printf 'plt%07d' "$NSTEPS")
+"$E2E/fcompare3d.ex" -a "$TMP/ref/$PLT" "$TMP/mx/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}.txt" 2>&1
+tail -3 "$OUTDIR/fcompare_cuda_${TAG}.txt"
+python3 - "$OUTDIR" "$TAG" <<'EOF'
+import json, re, sys
+out, tag = sys.argv[1:3]
+names = ["Maestro::MakeEdgeScal()", "Maestro::MakeRhoXFlux()", "Maestro::MakeRhoHFlux()",
+         "Maestro::UpdateScal()", "Maestro::Makew0()", "Maestro::CelltoEdge()",
+         "Maestro::DensityAdvance()", "Maestro::EnthalpyAdvance()", "Maestro::VelocityAdvance()",
+         "Maestro::AdvanceTimeStep()", "Maestro::Evolve()"]
+res = {}
+for arm in ("ref", "mx"):
+    txt = open(f"{out}/run_{tag}_{arm}.log").read()
+    # second TinyProfiler table = inclusive times: name ncalls min avg max pct
+    incl = txt.split("Incl.")[-1] if "Incl." in txt else ""
+    d = {}
+    for n in names:
+        m = re.search(re.escape(n) + r"\s+(\d+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)", incl)
+        if m:
+            d[n] = {"ncalls": int(m.group(1)), "incl_s": float(m.group(3))}
+    res[arm] = d
+fc = open(f"{out}/fcompare_cuda_{tag}.txt").read()
+worst = 0.0
+for line in fc.splitlines():
+    m = re.match(r"^\s(\S.*?)\s+([-+0-9.eE]+)\s+([-+0-9.eE]+)\s*$", line)
+    if m and not m.group(1).startswith("variable"):
+        worst = max(worst, float(m.group(3)))
+res["fcompare_max_rel"] = worst
+res["fcompare_agree"] = "PLOTFILE AGREE" in fc
+json.dump(res, open(f"{out}/cuda_compare_{tag}.json", "w"), indent=1)
+for n in names:
+    a, b = res["ref"].get(n), res["mx"].get(n)
+    if a and b:
+        print(f"{n:34s} ref {a['incl_s']:9.4f} s  mx {b['incl_s']:9.4f} s  x{a['incl_s'] / max(b['incl_s'], 1e-12):6.2f}  ({a['ncalls']} calls)")
+print("fcompare max rel", worst, "agree", res["fcompare_agree"])
+EOF
+rm -rf "$TMP"

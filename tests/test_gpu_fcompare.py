@@ -27,6 +27,9 @@ FCOMPARE_TOL = 1e-10  # north_star
 NSTEPS = 10
 
 
+_CACHE = {}
+
+
 def _table(tmp):
     dst = os.path.join(tmp, "helm_table.dat")
     with gzip.open(os.path.join(E2E, "helm_table.dat.gz"), "rb") as f, open(dst, "wb") as g:
@@ -63,28 +66,39 @@ def parse_fcompare(text):
     return out
 
 
-@pytest.mark.parametrize("dim,extra", [
-    (2, ()),                                   # inputs_2d_C as shipped: ppm_type 0
-    (2, ("maestro.ppm_type=1",)),
-    (2, ("maestro.ppm_type=2",)),
-    (3, ()),                                   # inputs_3d_C as shipped: 64x64x512, ppm_type 1
+# arm "mx": maestroex_b200/overlay (member-for-member drop-in); arm "fx": overlay +
+# overlay_fused (DensityAdvance / EnthalpyAdvance on mx_density_edge_flux /
+# mx_enthalpy_edge_flux, the fused kernels bench.py measures)
+@pytest.mark.parametrize("dim,arm,extra", [
+    (2, "mx", ()),                             # inputs_2d_C as shipped: ppm_type 0
+    (2, "mx", ("maestro.ppm_type=1",)),
+    (2, "mx", ("maestro.ppm_type=2",)),
+    (3, "mx", ()),                             # inputs_3d_C as shipped: 64x64x512, ppm_type 1
+    (3, "fx", ()),
+    (3, "fx", ("maestro.ppm_type=0", "amr.n_cell=32 32 256")),   # coarser grid: cheap
+    (3, "fx", ("maestro.ppm_type=2", "amr.n_cell=32 32 256")),
 ])
-def test_fcompare_10_steps(tmp_path, dim, extra):
-    for f in (f"Maestro{dim}d.ref.ex", f"Maestro{dim}d.mx.ex", f"fcompare{dim}d.ex",
+def test_fcompare_10_steps(tmp_path, tmp_path_factory, dim, arm, extra):
+    for f in (f"Maestro{dim}d.ref.ex", f"Maestro{dim}d.{arm}.ex", f"fcompare{dim}d.ex",
               "helm_table.dat.gz"):
         if not os.path.exists(os.path.join(E2E, f)):
             pytest.skip(f"oracle/_ref/e2e/{f} not built (oracle/e2e/build_e2e.sh {dim})")
     tmp = str(tmp_path)
-    table = _table(tmp)
-    pr, _ = _run(f"Maestro{dim}d.ref.ex", os.path.join(tmp, "ref"), dim, table, extra)
-    pm, _ = _run(f"Maestro{dim}d.mx.ex", os.path.join(tmp, "mx"), dim, table, extra)
+    if "table" not in _CACHE:
+        _CACHE["table"] = _table(str(tmp_path_factory.mktemp("helm")))
+    table = _CACHE["table"]
+    if (dim, extra) not in _CACHE:  # the reference run is shared by the arms compared with it
+        rdir = os.path.join(str(tmp_path_factory.mktemp("ref")), "ref")
+        _CACHE[(dim, extra)] = _run(f"Maestro{dim}d.ref.ex", rdir, dim, table, extra)[0]
+    pr = _CACHE[(dim, extra)]
+    pm, _ = _run(f"Maestro{dim}d.{arm}.ex", os.path.join(tmp, arm), dim, table, extra)
     r = subprocess.run([os.path.join(E2E, f"fcompare{dim}d.ex"), "-a", pr, pm],
                        capture_output=True, text=True, timeout=600)
     table_txt = r.stdout
     keep = os.environ.get("MXADV_FCOMPARE_OUT")
     if keep:
         os.makedirs(keep, exist_ok=True)
-        tag = f"{dim}d" + "".join("_" + e.split(".")[-1].replace(" ", "x") for e in extra)
+        tag = f"{dim}d" + ("" if arm == "mx" else "_fused") + "".join("_" + e.split(".")[-1].replace(" ", "x") for e in extra)
         open(os.path.join(keep, f"fcompare_{tag}.txt"), "w").write(table_txt + r.stderr)
     errs = parse_fcompare(table_txt)
     assert len(errs) >= 20, table_txt[-3000:]
