@@ -360,12 +360,13 @@ def run_mxadv(a):
         face = (en + 1) * en * en
         uface = (en + 3) * (en + 2) ** 2
         h2d = 8 * a.e2e_boxes * (C * cells_s + C * cells_f + 3 * uface + face      # density
-                                 + cells_s + cells_f + 3 * uface + 3 * face + 3 * face)  # enthalpy
+                                 + cells_s + cells_f + 3 * uface + 3 * face)  # enthalpy
         d2h = 8 * a.e2e_boxes * (3 * C * face + 3 * C * face + face + 3 * face + 3 * face)
         e2e = {"value": en ** 3 * (a.nspec + 2) * a.e2e_boxes * world / te, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "sample": f"{a.e2e_boxes} boxes of {en}^3 per step, pinned host fabs through "
-                         f"mx_density_edge_flux + mx_enthalpy_edge_flux, {nthr} host "
+                         f"mx_density_edge_flux + mx_enthalpy_edge_flux (z-slab pipeline: "
+                         f"H2D / kernel / D2H of consecutive slabs overlap), {nthr} host "
                          f"thread(s) / stream(s) with boxes in flight"}
 
     cpu = None

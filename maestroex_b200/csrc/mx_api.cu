@@ -5,8 +5,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
+#include <functional>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mx_common.h"
@@ -71,6 +75,12 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+#define MX_TRY_(expr)                   \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != MX_OK) return rc__; \
+    } while (0)
+
 // One API call's worth of device mirrors for host-resident arguments.
 class Session {
    public:
@@ -105,6 +115,11 @@ class Session {
         void* dev = nullptr;
         CUDA_OK(alloc(&dev, sizeof(double) * (size_t)d.sn * f->ncomp));
         d.p = static_cast<double*>(dev);
+        if (pipe_) {  // copies are issued slab by slab in run_slabs()
+            if (nc > 0 && (in || outp)) items_.push_back({f->p, d, c0, nc, in, outp, d.lo[2]});
+            *out = d;
+            return MX_OK;
+        }
         if (in && nc > 0) {
             CUDA_OK(cudaMemcpyAsync(d.p + (size_t)c0 * d.sn, f->p + (size_t)c0 * d.sn,
                                     sizeof(double) * (size_t)d.sn * nc, cudaMemcpyHostToDevice,
@@ -122,6 +137,10 @@ class Session {
     // extra upload of another component range into an existing host mirror
     int upload(const MxFab* f, const DFab& d, int c0, int nc) {
         if (is_device_ptr(f->p) || nc <= 0) return MX_OK;
+        if (pipe_) {
+            items_.push_back({f->p, d, c0, nc, true, false, d.lo[2]});
+            return MX_OK;
+        }
         CUDA_OK(cudaMemcpyAsync(d.p + (size_t)c0 * d.sn, f->p + (size_t)c0 * d.sn,
                                 sizeof(double) * (size_t)d.sn * nc, cudaMemcpyHostToDevice,
                                 st_));
@@ -129,6 +148,17 @@ class Session {
     }
     int download_later(const MxFab* f, const DFab& d, int c0, int nc) {
         if (is_device_ptr(f->p) || nc <= 0) return MX_OK;
+        if (pipe_) {
+            // an earlier upload of the same components makes the item read-modify-write
+            for (auto& it : items_) {
+                if (it.h == f->p && it.c0 == c0 && it.nc == nc) {
+                    it.out = true;
+                    return MX_OK;
+                }
+            }
+            items_.push_back({f->p, d, c0, nc, false, true, d.lo[2]});
+            return MX_OK;
+        }
         backs_.push_back({f->p + (size_t)c0 * d.sn, d.p + (size_t)c0 * d.sn,
                           sizeof(double) * (size_t)d.sn * nc});
         return MX_OK;
@@ -156,6 +186,14 @@ class Session {
     // copy results back to host fabs and wait (host callers get synchronous semantics)
     int finish() {
         CUDA_OK(cudaGetLastError());
+        if (pipe_) {  // deferred items that never went through run_slabs: whole components
+            for (auto& it : items_)
+                if (it.out)
+                    backs_.push_back({it.h + (size_t)it.c0 * it.g.sn, it.g.p + (size_t)it.c0 * it.g.sn,
+                                      sizeof(double) * (size_t)it.g.sn * it.nc});
+            items_.clear();
+            pipe_ = false;
+        }
         for (auto& b : backs_) {
             CUDA_OK(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st_));
         }
@@ -163,7 +201,147 @@ class Session {
         return MX_OK;
     }
 
+    // ---- slab pipeline for host-resident fabs -------------------------------------------
+    // A host caller's step is PCIe bound (928 B/zone-species of copies against ~60 B of HBM
+    // traffic per zone-species of kernel work), and the link is full duplex: the valid z range
+    // is cut into slabs and the uploads of slab s+1, the kernel of slab s and the downloads
+    // of slab s-1 overlap (uploads and kernels in the caller's stream, downloads in a second one).  Results are unchanged: the kernels are box invariant
+    // (tests/test_gpu_fullsize.py), every input plane is uploaded once, every written plane
+    // downloaded once.
+    void defer_copies() { pipe_ = true; }
+    bool deferred() const { return pipe_; }
+
+    // everything the deferred input items still owe, on the compute stream (leaves the
+    // pipeline: the caller continues with the unpipelined composition and finish())
+    int upload_rest() {
+        for (auto& it : items_) {
+            if (it.in) MX_TRY_(copy_planes(it, it.next, it.g.lo[2] + it.g.n[2] - 1, true, st_));
+        }
+        return MX_OK;
+    }
+
+    // launch(slab geometry) -> 0 ok, > 0 unsupported (only legal on the first slab), < 0 error
+    int run_slabs(const KGeom& kg, int reach, const std::function<int(const KGeom&)>& launch,
+                  int* rc_first) {
+        *rc_first = 0;
+        const int nz = kg.vhi[2] - kg.vlo[2] + 1;
+        int thick = (nz + 7) / 8;  // measured on 128^3 boxes: 32-plane slabs beat 8 and 16
+        if (thick < 32) thick = 32;
+        if (const char* e = getenv("MXADV_SLAB")) thick = atoi(e) > 0 ? atoi(e) : nz;
+        const int nslab = (nz + thick - 1) / thick;
+        static cudaStream_t s_out = nullptr;
+        if (!s_out) CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        std::vector<cudaEvent_t> ev(2 * nslab + 1);
+        for (auto& e : ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        // MXADV_TRACE=1: device timeline of the pipeline on stderr (debugging aid)
+        const bool trace = getenv("MXADV_TRACE") != nullptr;
+        std::vector<std::pair<const char*, cudaEvent_t> > marks;
+        auto mark = [&](const char* what, cudaStream_t st) {
+            if (!trace) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            marks.push_back({what, e});
+        };
+        int rc = MX_OK;
+        auto body = [&]() -> int {
+            // the mirrors were allocated (and the base-state tables written) in st_ order
+            mark("start", st_);
+            CUDA_OK(cudaEventRecord(ev[2 * nslab], st_));
+            CUDA_OK(cudaStreamWaitEvent(s_out, ev[2 * nslab], 0));
+            for (int s = 0; s < nslab; ++s) {
+                const bool first = s == 0, last = s == nslab - 1;
+                KGeom g = kg;
+                g.vlo[2] = kg.vlo[2] + s * thick;
+                g.vhi[2] = last ? kg.vhi[2] : g.vlo[2] + thick - 1;
+                g.skip_top_z = last ? 0 : 1;
+                // inputs (read-only and read-modify-write alike: with skip_top_z every plane is
+                // written by exactly one slab): each plane once, just ahead of its slab's kernel
+                // and IN THE COMPUTE STREAM.  A separate upload stream was measured
+                // (MXADV_TRACE=1) to buy nothing: the compute stream's wait on an event of the
+                // upload stream only resolved once that stream's whole queue had drained.  The
+                // downloads are the long pole (2.1x the upload bytes) and do overlap.
+                for (auto& it : items_) {
+                    if (!it.in) continue;
+                    const int top = it.g.lo[2] + it.g.n[2] - 1;
+                    const int hi = last ? top : std::min(top, g.vhi[2] + reach);
+                    MX_TRY_(copy_planes(it, it.next, hi, true, st_));
+                }
+                mark("h2d done", st_);
+                const int r = launch(g);
+                if (r != 0) {
+                    if (r > 0 && first) {
+                        *rc_first = r;
+                        return MX_OK;
+                    }
+                    return fail(MX_ERR_CUDA, "fused kernel launch failed in the slab pipeline");
+                }
+                mark("kernel done", st_);
+                CUDA_OK(cudaEventRecord(ev[2 * s + 1], st_));
+                CUDA_OK(cudaStreamWaitEvent(s_out, ev[2 * s + 1], 0));
+                mark("d2h may start", s_out);
+                for (auto& it : items_) {
+                    if (!it.out) continue;
+                    const int top = it.g.lo[2] + it.g.n[2] - 1;
+                    const int lo = first ? std::max(it.g.lo[2], kg.vlo[2]) : g.vlo[2];
+                    const int hi = last ? std::min(top, kg.vhi[2] + 1) : g.vhi[2];
+                    MX_TRY_(copy_planes(it, lo, hi, false, s_out));
+                }
+                mark("d2h done", s_out);
+            }
+            CUDA_OK(cudaStreamSynchronize(s_out));
+            CUDA_OK(cudaStreamSynchronize(st_));
+            CUDA_OK(cudaGetLastError());
+            return MX_OK;
+        };
+        rc = body();
+        if (rc != MX_OK) {  // never free mirrors under copies still in flight
+            cudaStreamSynchronize(s_out);
+            cudaStreamSynchronize(st_);
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (trace && !marks.empty()) {
+            for (auto& m : marks) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, marks[0].second, m.second);
+                fprintf(stderr, "[mxadv pipeline] %8.3f ms  %s\n", ms, m.first);
+                }
+            for (auto& m : marks) cudaEventDestroy(m.second);
+        }
+        if (rc == MX_OK && *rc_first == 0) {
+            items_.clear();
+            pipe_ = false;
+        }
+        return rc;
+    }
+
    private:
+    struct Item {
+        double* h;   // host fab
+        DFab g;      // its device mirror
+        int c0, nc;  // component range
+        bool in, out;
+        int next;    // first z plane not uploaded yet
+    };
+    // planes [k_lo, k_hi] of every component of the item, one contiguous copy per component
+    int copy_planes(Item& it, int k_lo, int k_hi, bool to_device, cudaStream_t st) {
+        const int top = it.g.lo[2] + it.g.n[2] - 1;
+        k_lo = std::max(k_lo, it.g.lo[2]);
+        k_hi = std::min(k_hi, top);
+        if (k_hi < k_lo) return MX_OK;
+        const size_t bytes = sizeof(double) * (size_t)it.g.sz * (k_hi - k_lo + 1);
+        for (int c = it.c0; c < it.c0 + it.nc; ++c) {
+            const size_t off = (size_t)c * it.g.sn + (size_t)(k_lo - it.g.lo[2]) * it.g.sz;
+            if (to_device)
+                CUDA_OK(cudaMemcpyAsync(it.g.p + off, it.h + off, bytes, cudaMemcpyHostToDevice, st));
+            else
+                CUDA_OK(cudaMemcpyAsync(it.h + off, it.g.p + off, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        if (to_device) it.next = std::max(it.next, k_hi + 1);
+        return MX_OK;
+    }
+    std::vector<Item> items_;
+    bool pipe_ = false;
     struct Back {
         double* host;
         const double* dev;
@@ -533,6 +711,11 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
                       rho0_predicted_edge, w0, nullptr, nullptr, nullptr, nullptr, &f));
     const KGeom kg = make_kgeom(geom);
     const int ng_s = epar->ppm_type == 2 ? 4 : 3;
+    const KEdge e = make_kedge(epar);
+    // host fabs: copy and compute slab by slab (Session::run_slabs)
+    if (!sph && fused_density_supported(kg, e, f) && !is_device_ptr(state->p) &&
+        kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE") && !getenv("MXADV_KERNEL"))
+        S.defer_copies();
     MX_TRY(check_cover(geom, state, ng_s, -1, "state"));
     MX_TRY(check_cover(geom, force, 1, -1, "force"));
     const int rho = fpar->rho_comp;
@@ -567,8 +750,18 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
         MX_TRY(stage_mac(S, geom, r0mac_old, mac.r0_old, "r0mac_old"));
         MX_TRY(stage_mac(S, geom, r0mac_new, mac.r0_new, "r0mac_new"));
     }
-    KEdge e = make_kedge(epar);
-    if (fused_density_supported(kg, e, f)) {
+    if (S.deferred()) {
+        int rc1 = 0;
+        MX_TRY(S.run_slabs(
+            kg, ng_s + 1,
+            [&](const KGeom& g) {
+                return fused_density(g, e, epar, rho_bccomp, f, a.state, a.sedge, sf, eta, a.umac,
+                                     a.force, mac, nullptr, S.stream());
+            },
+            &rc1));
+        if (rc1 == 0) return S.finish();
+        MX_TRY(S.upload_rest());  // component set the fused kernel does not take: compose below
+    } else if (fused_density_supported(kg, e, f)) {
         // spherical: the time-centred rho0 on faces is species independent; form it once
         // (3 x 8 B/zone of workspace) instead of twice per face and species inside the kernel
         double* r0e[3] = {nullptr, nullptr, nullptr};
@@ -626,6 +819,10 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
     MX_TRY(fill_kflux(S, fpar, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, nullptr, nullptr,
                       rhoh0_old, rhoh0_edge_old, rhoh0_new, rhoh0_edge_new, &f));
     const KGeom kg = make_kgeom(geom);
+    const KEdge e = make_kedge(epar);
+    if (fused_enthalpy_supported(kg, e, f) && !is_device_ptr(state->p) &&
+        kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE") && !getenv("MXADV_KERNEL"))
+        S.defer_copies();
     EdgeArgs a;
     MX_TRY(stage_edge_args(S, geom, state, sedge, umac, force, epar, &a));
     DFab sf[3];
@@ -633,11 +830,22 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
     memset(&mac, 0, sizeof(mac));
     for (int d = 0; d < 3; ++d) {
         MX_TRY(check_cover(geom, &sflux[d], 0, d, "sflux"));
-        MX_TRY(S.fab(&sflux[d], &sf[d], fpar->rhoh_comp, 1, true, true));
+        MX_TRY(S.fab(&sflux[d], &sf[d], fpar->rhoh_comp, 1, !exact_face_box(geom, &sflux[d], d),
+                     true));
         MX_TRY(S.upload(&sedge[d], a.sedge[d], fpar->rho_comp, 1));
     }
-    KEdge e = make_kedge(epar);
-    if (fused_enthalpy_supported(kg, e, f)) {
+    if (S.deferred()) {
+        int rc1 = 0;
+        MX_TRY(S.run_slabs(
+            kg, (epar->ppm_type == 2 ? 4 : 3) + 1,
+            [&](const KGeom& g) {
+                return fused_enthalpy(g, e, epar, f, a.state, a.sedge, sf, a.umac, a.force,
+                                      S.stream());
+            },
+            &rc1));
+        if (rc1 == 0) return S.finish();
+        MX_TRY(S.upload_rest());
+    } else if (fused_enthalpy_supported(kg, e, f)) {
         const int rc =
             fused_enthalpy(kg, e, epar, f, a.state, a.sedge, sf, a.umac, a.force, S.stream());
         if (rc == 0) return S.finish();

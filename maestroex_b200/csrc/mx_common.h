@@ -39,11 +39,15 @@ struct KGeom {
     int vlo[3], vhi[3];  // valid cell box
     int dlo[3], dhi[3];  // domain
     double dx[3];
+    // 1: the streaming kernel leaves the z faces at vhi[2]+1 to the box above (the slab
+    // pipeline of mx_api.cu: every face plane is then written by exactly one slab)
+    int skip_top_z;
 };
 
 inline KGeom make_kgeom(const MxGeom* g) {
     KGeom k;
     k.dim = g->dim;
+    k.skip_top_z = 0;
     for (int d = 0; d < 3; ++d) {
         const bool in = d < g->dim;
         k.vlo[d] = in ? g->valid_lo[d] : 0;

@@ -78,7 +78,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     const int i = x0 - 1 + tx, j = y0 - 1 + ty;
     int k0, k1;  // this block's z chunk, k1 exclusive
     chunk_range(A, blockIdx.y, k0, k1);
-    const bool last = (k1 == g.vhi[2] + 1);
+    const bool last = (k1 == g.vhi[2] + 1) && !g.skip_top_z;
     const int a0 = k0 - 1;
 
     // faces this thread stores: the tile's low faces, plus the high face only on the last tile

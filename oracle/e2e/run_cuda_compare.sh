@@ -6,6 +6,9 @@
 #   * the TinyProfiler inclusive times of the hot-path members in both runs
 #     (tiny_profiler.device_synchronize_around_region=1, so a region's time is the device time
 #     of the work it launched).
+# amrex.the_arena_is_managed=1: the reference fills physical boundaries on the host
+# (Maestro::ScalarFill -> amrex::fab_filcc, Source/MaestroBCFill.cpp:17), which segfaults on
+# AMReX 24.08's default device-only arena; with managed fabs the unmodified reference runs.
 # usage: run_cuda_compare.sh OUTDIR TAG [extra ParmParse arguments...]
 set -uo pipefail
 OUTDIR=$1; TAG=$2; shift 2
@@ -24,7 +27,8 @@ for arm in ref mx; do
     ln -s "$TMP/helm_table.dat" "$TMP/$arm/helm_table.dat"
     (cd "$TMP/$arm" && timeout 900 "$E2E/Maestro3d.cuda.$arm.ex" inputs_3d_C \
         maestro.max_step=$NSTEPS maestro.plot_int=$NSTEPS maestro.chk_int=-1 maestro.plot_deltat=-1 \
-        tiny_profiler.device_synchronize_around_region=1 amrex.fpe_trap_invalid=0 "$@" \
+        tiny_profiler.device_synchronize_around_region=1 amrex.fpe_trap_invalid=0 \
+        amrex.the_arena_is_managed=1 amrex.the_arena_init_size=4294967296 "$@" \
         > "$OUTDIR/run_${TAG}_$arm.log" 2>&1; echo "rc=$?" >> "$OUTDIR/run_${TAG}_$arm.log")
     tail -1 "$OUTDIR/run_${TAG}_$arm.log"
 done
