@@ -48,6 +48,7 @@ struct FusedArgs {
     double h[3], inv_h[3];
     int inv_exact[3];  // h_d is a power of two: x / h_d == x * inv_h_d exactly
     int slope_order;
+    int is_vel;  // velocity sweep: outflow clamp of the normal component at physical faces
     DFab state, force, sedge[3], umac[3], sflux[3], eta;
     DFab r0o[3], r0n[3];
     double* r0e[3];  // spherical: 0.5*(r0mac_old + r0mac_new) laid out like one sedge[d] component
@@ -682,6 +683,7 @@ void fill_common(FusedArgs& A, const KGeom& g, const KEdge& e, const DFab& state
                  const DFab* sedge, const DFab* umac, const DFab& force) {
     memset(&A, 0, sizeof(A));
     A.g = g;
+    A.is_vel = e.is_vel;
     A.dt = e.dt;
     A.eps = e.eps;
     A.dt2 = 0.5 * e.dt;
@@ -730,7 +732,8 @@ bool comps_ok(const MxEdgeParams* par, int first_bccomp, int ncomp, bool* any_bc
 
 bool fused_edge_supported(const KGeom& g, const KEdge& e) {
     if (getenv("MXADV_FORCE_STAGED")) return false;
-    return g.dim == 3 && !e.is_vel && !e.is_cons && !e.trace;
+    // velocity sweeps (is_vel): k_stream4 only (the A/B kernels have no normal-velocity clamp)
+    return g.dim == 3 && (!e.is_vel || !getenv("MXADV_KERNEL")) && !e.is_cons && !e.trace;
 }
 
 int fused_edge_scal(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, const DFab& state,

@@ -181,6 +181,10 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
         const int bclz = A.bclo[n][2], bchz = A.bchi[n][2];
         const bool lobcz = BC && (bclz == BC_EXT_DIR || bclz == BC_HOEXTRAP);
         const bool hibcz = BC && (bchz == BC_EXT_DIR || bchz == BC_HOEXTRAP);
+        // is_vel: the normal velocity component is clamped at outflow faces
+        // (MaestroMakeEdgeScalars.cpp:716-728 and the same blocks of the later stages)
+        const bool vcx = BC && A.is_vel && comp == 0, vcy = BC && A.is_vel && comp == 1,
+                   vcz = BC && A.is_vel && comp == 2;
         const bool flux1 = (MODE == 1 && n > 0);
         const bool first_spec = (n == 1);
         const bool is_spec =
@@ -431,9 +435,9 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             }
             ipz_prev = ipz;
             if (BC) {
-                bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, slx, srx);
-                bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, sly, sry);
-                bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, slz, srz);
+                bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, slx, srx);
+                bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, sly, sry);
+                bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, slz, srz);
             }
             const double shx = upw(px_pos, px_nz0, slow, slx, srx);  // QUIRK: |u| > 0.0 (:746)
             const double shy = upw(py_pos, py_nz0, slow, sly, sry);
@@ -452,7 +456,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                     l = ipy;
                     r = X_SY[tid + GX];
                 }
-                if (BC) bc_pair(j + 1, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(j + 1, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
                 shy_up = upw(py2_pos, py2_nz0, slow, l, r);
             }
 
@@ -506,27 +510,27 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             double hxy, hyx, hzx, hzy, hxz, hyz;
             {
                 double l = slx - shfl_up1(t6y), r = srx - t6y;
-                if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, l, r);
                 hxy = upw(px_pos, px_nz, slow, l, r);
                 l = sly - X_T6X[tid - GX];
                 r = sry - t6x;
-                if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
                 hyx = upw(py_pos, py_nz, slow, l, r);
                 l = slz - HS(H_T6X);
                 r = srz - t6x;
-                if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, l, r);
                 hzx = upw(pz_pos, pz_nz, slow, l, r);
                 l = slz - HS(H_T6Y);
                 r = srz - t6y;
-                if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, l, r);
                 hzy = upw(pz_pos, pz_nz, slow, l, r);
                 l = slx_p - shfl_up1(tz);
                 r = srx_p - tz;
-                if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, l, r);
                 hxz = upw(qx_pos, qx_nz, slow, l, r);
                 l = sly_p - X_TZ[tid - GX];
                 r = sry_p - tz;
-                if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, l, r);
+                if (BC) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
                 hyz = upw(qy_pos, qy_nz, slow, l, r);
             }
             HS(H_T6X) = t6x;
@@ -560,13 +564,13 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                     const double el = ((slx_p - shfl_up1(t4yz)) - shfl_up1(t4zy)) + shfl_up1(fs_prev);
                     const double er = ((srx_p - t4yz) - t4zy) + fs_prev;
                     ex_v = upw(qx_pos, qx_nz, slow, el, er);
-                    if (BC) ex_v = bc_final(i, g.dlo[0], g.dhi[0], bclx, bchx, false, 0.0, 0.0, el, er, ex_v);
+                    if (BC) ex_v = bc_final(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, el, er, ex_v);
                 }
                 {
                     const double el = ((sly_p - X_QY1[tid - GX]) - X_QY2[tid - GX]) + X_FS[tid - GX];
                     const double er = ((sry_p - t4xz) - t4zx) + fs_prev;
                     ey_v = upw(qy_pos, qy_nz, slow, el, er);
-                    if (BC) ey_v = bc_final(j, g.dlo[1], g.dhi[1], bcly, bchy, false, 0.0, 0.0, el, er, ey_v);
+                    if (BC) ey_v = bc_final(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, el, er, ey_v);
                 }
                 if (ownx) pEx[0] = ex_v;
                 if (owny) pEy[0] = ey_v;
@@ -602,7 +606,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             const double er_z = ((srz - t4xy) - t4yx) + fs_cur;
             if (do_z) {  // block uniform: z face a
                 double ez_v = upw(pz_pos, pz_nz, slow, el_z, er_z);
-                if (BC) ez_v = bc_final(a, g.dlo[2], g.dhi[2], bclz, bchz, false, 0.0, 0.0, el_z, er_z, ez_v);
+                if (BC) ez_v = bc_final(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, el_z, er_z, ez_v);
                 if (ownz) pEz[0] = ez_v;
                 if (MODE == 1 && flux1) {
                     double r0z;

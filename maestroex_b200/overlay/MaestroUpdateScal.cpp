@@ -31,6 +31,22 @@ void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& sta
     par.num_comp = num_comp;
 
     for (int lev = 0; lev <= finest_level; ++lev) {
+#ifdef AMREX_USE_GPU
+        // zone flags of all local boxes of this level in one device allocation (1 byte per
+        // zone): consecutive MFIter iterations run on different AMReX streams, so the boxes
+        // must not share a buffer, and a per-box allocation would cost a synchronisation each
+        const bool want_mask = (start_comp == RhoH) && do_eos_h_above_cutoff;
+        std::vector<Long> mask_off;
+        Long mask_total = 0;
+        if (want_mask) {
+            for (MFIter mfi(stateold[lev], false); mfi.isValid(); ++mfi) {
+                mask_off.push_back(mask_total);
+                mask_total += mfi.validbox().numPts();
+            }
+        }
+        Gpu::DeviceVector<unsigned char> dmask(mask_total);
+        int ibox = 0;
+#endif
         for (MFIter mfi(stateold[lev], false); mfi.isValid(); ++mfi) {
             const Box& vbx = mfi.validbox();
             const MxGeom g = mxadv::geom_of(geom[lev], vbx);
@@ -43,17 +59,15 @@ void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& sta
             // GPU AMReX: fabs are device memory.  The zone flags stay on the device and the
             // reference's own eos() runs there, on the flagged zones, in AMReX's stream
             // (same statements as :137-159)
-            Gpu::DeviceVector<unsigned char> dmask;
-            if (enth && do_eos_h_above_cutoff) dmask.resize(vbx.numPts());
-            mxadv::check(mx_update_scal(&g, &so, &sn, sf.f, &fo, &par,
-                                        dmask.empty() ? nullptr : dmask.data(), nullptr,
+            unsigned char* mk_box = want_mask ? dmask.data() + mask_off[ibox++] : nullptr;
+            mxadv::check(mx_update_scal(&g, &so, &sn, sf.f, &fo, &par, mk_box, nullptr,
                                         mxadv::stream()),
                          "UpdateScal");
-            if (!dmask.empty()) {
+            if (mk_box != nullptr) {
                 const Array4<const Real> sold_arr = stateold[lev].const_array(mfi);
                 const Array4<Real> snew_arr = statenew[lev].array(mfi);
                 const Array4<const Real> p0_arr = p0_cart[lev].const_array(mfi);
-                const unsigned char* AMREX_RESTRICT mk = dmask.data();
+                const unsigned char* AMREX_RESTRICT mk = mk_box;
                 const Dim3 vlo = amrex::lbound(vbx);
                 const Dim3 vln = amrex::length(vbx);
                 ParallelFor(vbx, [=] AMREX_GPU_DEVICE(int i, int j, int k) {
@@ -70,7 +84,6 @@ void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& sta
                     eos(eos_input_rp, eos_state);
                     snew_arr(i, j, k, RhoH) = snew_arr(i, j, k, Rho) * eos_state.h;
                 });
-                Gpu::streamSynchronize();  // dmask is freed at the end of this iteration
             }
 #else
             std::vector<unsigned char> mask;
@@ -110,6 +123,9 @@ void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& sta
             }
 #endif
         }
+#ifdef AMREX_USE_GPU
+        if (want_mask) Gpu::streamSynchronizeAll();  // dmask goes out of scope
+#endif
     }
 
     // :257-296, unchanged: AMR synchronisation and ghost fill

@@ -72,6 +72,24 @@ open("GNUmakefile", "w").write(mk.replace(inc, add + inc + tail))
 EOF
 $MK > build_mx.log 2>&1
 cp Maestro3d.gnu.TPROF.CUDA.ex "$OUT/Maestro3d.cuda.mx.ex"
+# 3. the fused overlay on top (DensityAdvance / EnthalpyAdvance on the fused kernels)
+rm -rf "$WORK/rb_cudafx3"
+cp -r "$WORK/rb_cudamx3" "$WORK/rb_cudafx3"
+cd "$WORK/rb_cudafx3"
+rm -f Maestro3d.gnu.TPROF.CUDA.ex
+for f in MaestroDensityAdvance MaestroEnthalpyAdvance; do
+    find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
+done
+python3 - <<'EOF'
+mk = open("GNUmakefile").read()
+key = "LIBRARIES         += -lmxadv"
+add = """Bpack   += $(MXADV_HOME)/maestroex_b200/overlay_fused/Make.package
+Blocs   += $(MXADV_HOME)/maestroex_b200/overlay_fused
+"""
+open("GNUmakefile", "w").write(mk.replace(key, add + key))
+EOF
+$MK > build_fx.log 2>&1
+cp Maestro3d.gnu.TPROF.CUDA.ex "$OUT/Maestro3d.cuda.fx.ex"
 cp "$WORK/rb_cuda3/inputs_3d_C" "$WORK/rb_cuda3/model.hse.cool.coulomb" "$OUT/"
 [ -f "$OUT/helm_table.dat.gz" ] || gzip -c "$REF/external/Microphysics/EOS/helmholtz/helm_table.dat" > "$OUT/helm_table.dat.gz"
 strip "$OUT"/Maestro3d.cuda.*.ex

@@ -15,13 +15,14 @@ OUTDIR=$1; TAG=$2; shift 2
 REPO=$(cd "$(dirname "$0")/../.." && pwd)
 E2E=$REPO/oracle/_ref/e2e
 NSTEPS=${NSTEPS:-10}
+ARMS=${ARMS:-"ref mx fx"}
 NVTXDIR=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nvtx/lib
 export LD_LIBRARY_PATH=$REPO/maestroex_b200/csrc:$NVTXDIR:${LD_LIBRARY_PATH:-}
 mkdir -p "$OUTDIR"
 OUTDIR=$(cd "$OUTDIR" && pwd)
 TMP=$(mktemp -d)
 gunzip -c "$E2E/helm_table.dat.gz" > "$TMP/helm_table.dat"
-for arm in ref mx; do
+for arm in $ARMS; do
     mkdir -p "$TMP/$arm"
     cp "$E2E/inputs_3d_C" "$E2E/model.hse.cool.coulomb" "$TMP/$arm/"
     ln -s "$TMP/helm_table.dat" "$TMP/$arm/helm_table.dat"
@@ -30,11 +31,15 @@ for arm in ref mx; do
         tiny_profiler.device_synchronize_around_region=1 amrex.fpe_trap_invalid=0 \
         amrex.the_arena_is_managed=1 amrex.the_arena_init_size=4294967296 "$@" \
         > "$OUTDIR/run_${TAG}_$arm.log" 2>&1; echo "rc=$?" >> "$OUTDIR/run_${TAG}_$arm.log")
-    tail -1 "$OUTDIR/run_${TAG}_$arm.log"
+    tail -n 1 "$OUTDIR/run_${TAG}_$arm.log"
 done
 PLT=$(printf 'plt%07d' "$NSTEPS")
 "$E2E/fcompare3d.ex" -a "$TMP/ref/$PLT" "$TMP/mx/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}.txt" 2>&1
-tail -3 "$OUTDIR/fcompare_cuda_${TAG}.txt"
+tail -n 1 "$OUTDIR/fcompare_cuda_${TAG}.txt"
+if [ -d "$TMP/fx/$PLT" ]; then  # the two overlay builds must agree exactly
+    "$E2E/fcompare3d.ex" -a "$TMP/mx/$PLT" "$TMP/fx/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}_mx_vs_fx.txt" 2>&1
+    tail -n 1 "$OUTDIR/fcompare_cuda_${TAG}_mx_vs_fx.txt"
+fi
 python3 - "$OUTDIR" "$TAG" <<'EOF'
 import json, re, sys
 out, tag = sys.argv[1:3]
@@ -43,7 +48,9 @@ names = ["Maestro::MakeEdgeScal()", "Maestro::MakeRhoXFlux()", "Maestro::MakeRho
          "Maestro::DensityAdvance()", "Maestro::EnthalpyAdvance()", "Maestro::VelocityAdvance()",
          "Maestro::AdvanceTimeStep()", "Maestro::Evolve()"]
 res = {}
-for arm in ("ref", "mx"):
+import os
+arms = [a for a in ("ref", "mx", "fx") if os.path.exists(f"{out}/run_{tag}_{a}.log")]
+for arm in arms:
     txt = open(f"{out}/run_{tag}_{arm}.log").read()
     # second TinyProfiler table = inclusive times: name ncalls min avg max pct
     incl = txt.split("Incl.")[-1] if "Incl." in txt else ""
@@ -63,9 +70,15 @@ res["fcompare_max_rel"] = worst
 res["fcompare_agree"] = "PLOTFILE AGREE" in fc
 json.dump(res, open(f"{out}/cuda_compare_{tag}.json", "w"), indent=1)
 for n in names:
-    a, b = res["ref"].get(n), res["mx"].get(n)
-    if a and b:
-        print(f"{n:34s} ref {a['incl_s']:9.4f} s  mx {b['incl_s']:9.4f} s  x{a['incl_s'] / max(b['incl_s'], 1e-12):6.2f}  ({a['ncalls']} calls)")
+    a = res["ref"].get(n)
+    if not a:
+        continue
+    line = f"{n:30s} ref {a['incl_s']:8.4f} s"
+    for arm in arms[1:]:
+        b = res[arm].get(n)
+        if b:
+            line += f" | {arm} {b['incl_s']:8.4f} s x{a['incl_s'] / max(b['incl_s'], 1e-12):5.2f}"
+    print(line + f"  ({a['ncalls']} calls)")
 print("fcompare max rel", worst, "agree", res["fcompare_agree"])
 EOF
 rm -rf "$TMP"
