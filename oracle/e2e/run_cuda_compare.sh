@@ -34,12 +34,17 @@ for arm in $ARMS; do
     tail -n 1 "$OUTDIR/run_${TAG}_$arm.log"
 done
 PLT=$(printf 'plt%07d' "$NSTEPS")
-"$E2E/fcompare3d.ex" -a "$TMP/ref/$PLT" "$TMP/mx/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}.txt" 2>&1
-tail -n 1 "$OUTDIR/fcompare_cuda_${TAG}.txt"
-if [ -d "$TMP/fx/$PLT" ]; then  # the two overlay builds must agree exactly
-    "$E2E/fcompare3d.ex" -a "$TMP/mx/$PLT" "$TMP/fx/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}_mx_vs_fx.txt" 2>&1
-    tail -n 1 "$OUTDIR/fcompare_cuda_${TAG}_mx_vs_fx.txt"
-fi
+LAST=ref
+for arm in $ARMS; do  # reference build against each overlay build; overlay builds against each other
+    [ "$arm" = ref ] && continue
+    "$E2E/fcompare3d.ex" -a "$TMP/ref/$PLT" "$TMP/$arm/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}_ref_vs_$arm.txt" 2>&1
+    tail -n 1 "$OUTDIR/fcompare_cuda_${TAG}_ref_vs_$arm.txt"
+    if [ "$LAST" != ref ]; then
+        "$E2E/fcompare3d.ex" -a "$TMP/$LAST/$PLT" "$TMP/$arm/$PLT" > "$OUTDIR/fcompare_cuda_${TAG}_${LAST}_vs_$arm.txt" 2>&1
+        tail -n 1 "$OUTDIR/fcompare_cuda_${TAG}_${LAST}_vs_$arm.txt"
+    fi
+    LAST=$arm
+done
 python3 - "$OUTDIR" "$TAG" <<'EOF'
 import json, re, sys
 out, tag = sys.argv[1:3]
@@ -60,7 +65,7 @@ for arm in arms:
         if m:
             d[n] = {"ncalls": int(m.group(1)), "incl_s": float(m.group(3))}
     res[arm] = d
-fc = open(f"{out}/fcompare_cuda_{tag}.txt").read()
+fc = open(f"{out}/fcompare_cuda_{tag}_ref_vs_{arms[-1]}.txt").read()
 worst = 0.0
 for line in fc.splitlines():
     m = re.match(r"^\s(\S.*?)\s+([-+0-9.eE]+)\s+([-+0-9.eE]+)\s*$", line)
