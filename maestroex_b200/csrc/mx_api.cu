@@ -229,7 +229,9 @@ class Session {
         if (thick < 32) thick = 32;
         if (const char* e = getenv("MXADV_SLAB")) thick = atoi(e) > 0 ? atoi(e) : nz;
         const int nslab = (nz + thick - 1) / thick;
-        static cudaStream_t s_out = nullptr;
+        // one download stream per calling host thread (an OpenMP caller has a box in flight per
+        // thread; sharing the stream would make every call wait for the others' copies)
+        thread_local cudaStream_t s_out = nullptr;
         if (!s_out) CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         std::vector<cudaEvent_t> ev(2 * nslab + 1);
         for (auto& e : ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
