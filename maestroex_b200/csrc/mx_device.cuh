@@ -232,7 +232,9 @@ MXD void ppm1_finish(const double* S, int I, int lo, int hi, bool lobc, bool hib
     sp = sp_u;
     const double sedgel = sp, sedger = sm;
     cw_limit(s0, sm, sp);
-    if (BC) {
+    // (lobc / hibc are uniform over a warp in the streaming kernel, which clears them away
+    // from the domain faces: the whole block below is then skipped by a uniform branch)
+    if (BC && (lobc || hibc)) {
         if (I == lo) {
             if (lobc) {
                 sm = sm1;
