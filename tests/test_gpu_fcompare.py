@@ -77,6 +77,8 @@ def parse_fcompare(text):
     (3, "fx", ()),
     (3, "fx", ("maestro.ppm_type=0", "amr.n_cell=32 32 256")),   # coarser grid: cheap
     (3, "fx", ("maestro.ppm_type=2", "amr.n_cell=32 32 256")),
+    # boxes of 32 x 32 x 64: the host-fab z-slab pipeline runs with two slabs per box
+    (3, "fx", ("amr.n_cell=32 32 256", "amr.max_grid_size=64")),
 ])
 def test_fcompare_10_steps(tmp_path, tmp_path_factory, dim, arm, extra):
     for f in (f"Maestro{dim}d.ref.ex", f"Maestro{dim}d.{arm}.ex", f"fcompare{dim}d.ex",
