@@ -24,6 +24,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_tma_launches{0};
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -51,16 +52,18 @@ int require_device() {
                     "no CUDA device available; libmxadv has no CPU fallback (%s)",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     }
-    static bool pool_init = false;
-    if (!pool_init) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    // per device (a single process may drive several GPUs): bit d set = pool of device d tuned
+    static std::atomic<unsigned long long> pool_init{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(pool_init.load(std::memory_order_relaxed) & bit)) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long thr = ~0ull;  // keep freed workspace cached in the pool
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
-        pool_init = true;
+        pool_init.fetch_or(bit, std::memory_order_relaxed);
     }
     return MX_OK;
 }
@@ -231,17 +234,34 @@ class Session {
         const int nslab = (nz + thick - 1) / thick;
         // one download stream per calling host thread (an OpenMP caller has a box in flight per
         // thread; sharing the stream would make every call wait for the others' copies)
-        thread_local cudaStream_t s_out = nullptr;
+        // ... and per device: a stream belongs to the device that was current at its creation
+        constexpr int MAXDEV = 64;
+        thread_local cudaStream_t s_outs[MAXDEV] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaStream_t& s_out = s_outs[dev & (MAXDEV - 1)];
         if (!s_out) CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        std::vector<cudaEvent_t> ev(2 * nslab + 1);
-        for (auto& e : ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        // events live in a holder so that every early return below destroys them
+        struct Events {
+            std::vector<cudaEvent_t> v;
+            ~Events() {
+                for (auto e : v) cudaEventDestroy(e);
+            }
+        } evs, mks;
+        for (int q = 0; q < 2 * nslab + 1; ++q) {
+            cudaEvent_t e;
+            CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            evs.v.push_back(e);
+        }
+        std::vector<cudaEvent_t>& ev = evs.v;
         // MXADV_TRACE=1: device timeline of the pipeline on stderr (debugging aid)
         const bool trace = getenv("MXADV_TRACE") != nullptr;
         std::vector<std::pair<const char*, cudaEvent_t> > marks;
         auto mark = [&](const char* what, cudaStream_t st) {
             if (!trace) return;
             cudaEvent_t e;
-            cudaEventCreate(&e);
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            mks.v.push_back(e);
             cudaEventRecord(e, st);
             marks.push_back({what, e});
         };
@@ -301,14 +321,12 @@ class Session {
             cudaStreamSynchronize(s_out);
             cudaStreamSynchronize(st_);
         }
-        for (auto& e : ev) cudaEventDestroy(e);
         if (trace && !marks.empty()) {
             for (auto& m : marks) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, marks[0].second, m.second);
                 fprintf(stderr, "[mxadv pipeline] %8.3f ms  %s\n", ms, m.first);
-                }
-            for (auto& m : marks) cudaEventDestroy(m.second);
+            }
         }
         if (rc == MX_OK && *rc_first == 0) {
             items_.clear();
@@ -509,6 +527,7 @@ int need_base(const MxBase* b, const char* name) {
 }  // namespace
 
 void mx_count_launch(int n) { g_launches += n; }
+void mx_count_tma_launch() { g_tma_launches += 1; }
 
 extern "C" {
 
@@ -525,7 +544,11 @@ int mx_device_count(void) {
 }
 
 long long mx_launch_count(void) { return g_launches.load(); }
-void mx_reset_launch_count(void) { g_launches = 0; }
+void mx_reset_launch_count(void) {
+    g_launches = 0;
+    g_tma_launches = 0;
+}
+long long mx_tma_launch_count(void) { return g_tma_launches.load(); }
 
 int mx_free_workspace(void) {
     MX_TRY(require_device());

@@ -79,5 +79,6 @@ struct KFlux {
 };
 
 void mx_count_launch(int n = 1);
+void mx_count_tma_launch();
 
 #endif

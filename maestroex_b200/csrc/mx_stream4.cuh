@@ -701,12 +701,16 @@ __global__ void __launch_bounds__(32 * S4_GY, S4_MINB) k_stream4(const __grid_co
 template <int PPM, int MODE, bool SPH>
 int launch_stream4(const FusedArgs& A, cudaStream_t stream) {
     const size_t smem = sizeof(double) * (size_t)stream4_smem_doubles<PPM>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    // cudaFuncSetAttribute is per device: remember which devices have it (bit d of the mask)
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load(std::memory_order_relaxed) & bit)) {
         if (cudaFuncSetAttribute(k_stream4<PPM, MODE, SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
-        attr_set = true;
+        attr_set.fetch_or(bit, std::memory_order_relaxed);
     }
     dim3 grid(A.ntx * A.nty, A.nzc);
     k_stream4<PPM, MODE, SPH><<<grid, 32 * S4_GY, smem, stream>>>(A);

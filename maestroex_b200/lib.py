@@ -46,6 +46,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     lib.mx_last_error.restype = C.c_char_p
     lib.mx_launch_count.restype = C.c_longlong
+    lib.mx_tma_launch_count.restype = C.c_longlong
     lib.mx_halo_count.restype = C.c_longlong
     return lib
 

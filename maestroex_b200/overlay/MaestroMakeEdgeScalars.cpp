@@ -46,7 +46,7 @@ void Maestro::MakeEdgeScal(Vector<MultiFab>& state,
 
     // we use this to prevent the creation of edge states which differ across levels
     // (Source/MaestroMakeEdgeScalars.cpp:297-301; AMR stays the reference's own code)
-    if (is_vel && reflux_type == 1) {
+    if (is_vel && (reflux_type == 1 || reflux_type == 2)) {
         AverageDownFaces(sedge);
     }
 }

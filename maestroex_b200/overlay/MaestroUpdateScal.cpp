@@ -7,6 +7,14 @@
 // the zones the library flags; the AMR / ghost-fill tail (:257-296) is unchanged.
 #include <MxadvAmrex.H>
 
+// mx_update_scal carries no auxiliary composition variables: the reference updates them in
+// the species branch (Source/MaestroAdvection.cpp:203-211) and fills eos_state.aux before
+// eos() (:148-153).  Refuse to build against a network that has them instead of silently
+// producing a wrong statenew.
+#if defined(NAUX_NET) && NAUX_NET > 0
+#error "maestroex_b200 overlay: UpdateScal does not handle NAUX_NET > 0 (auxiliary variables); build this problem with Source/MaestroAdvection.cpp"
+#endif
+
 using namespace amrex;
 
 void Maestro::UpdateScal(const Vector<MultiFab>& stateold, Vector<MultiFab>& statenew,

@@ -1,0 +1,45 @@
+#!/bin/bash
+# scripts/gpu.sh <task> [args]  — the GPU-box jobs of this repo, one parametrised script.
+# Run as: gpurun --timeout N -- 'scripts/gpu.sh <task> ...'.  Everything is wrapped in its own
+# `timeout` so that a hung kernel cannot hold the box.  Output goes to gpurun_out/<tag>/.
+set -u
+task=${1:-help}; shift || true
+tag=${TAG:-$task}
+out=gpurun_out/$tag
+mkdir -p $out
+bench() {  # bench <label> <env...> -- <bench args>
+  local label=$1; shift
+  local envs=()
+  while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout -k 10 900 python bench.py "$@" > $out/bench_$label.json 2> $out/bench_$label.err
+  python - "$out/bench_$label.json" "$label" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r = d.get("roofline", {})
+    print(f"{sys.argv[2]:28s} value {d['value']:.4g} ms/step {d['ms_per_step']:.2f} density-launch {r.get('ms_per_launch')} frac {r.get('frac')} e2e {d.get('e2e', {}).get('value')}")
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
+PY
+}
+case $task in
+  k6first)   # first contact of a new kernel: parity of the new kernel, then A/B timing
+    timeout -k 10 900 python -m pytest tests/test_gpu_stream6.py -x -q -m gpu 2>&1 | tail -15 | tee $out/pytest_stream6.log
+    bench 256_v4 MXADV_KERNEL=v4 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
+    bench 256_k6 X=1 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
+    bench 256_fmad_k6 MXADV_LIB=exp/fmad/libmxadv.so -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
+    bench 256_fmad_v4 MXADV_LIB=exp/fmad/libmxadv.so MXADV_KERNEL=v4 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
+    bench 512_k6 X=1 -- --size 512 --steps 5 --warmup 3 --no-cpu --no-e2e
+    ;;
+  tests)     # the whole GPU suite
+    timeout -k 10 ${T:-2400} python -m pytest tests -x -q -m gpu "$@" 2>&1 | tail -25 | tee $out/pytest_gpu.log
+    ;;
+  ab)        # A/B of experiment builds: scripts/gpu.sh ab <size> <name1> <name2> ...   (exp/<name>/libmxadv.so; "tree" = in-tree)
+    size=$1; shift
+    for name in "$@"; do
+      if [ "$name" = tree ]; then lib=maestroex_b200/csrc/libmxadv.so; else lib=exp/$name/libmxadv.so; fi
+      bench ${size}_$name MXADV_LIB=$lib -- --size $size --steps 5 --warmup 3 --no-cpu --no-e2e ${BENCH_ARGS:-}
+    done
+    ;;
+  *) echo "tasks: k6first | tests | ab <size> <names...>"; exit 2;;
+esac

@@ -8,6 +8,11 @@ from maestroex_b200.synth import FIRSTSPEC, RHO, RHOH, make_problem  # noqa: F40
 
 # north_star: "edge states and fluxes must agree to a maximum relative error of 1e-12 per zone"
 REL_TOL = 1.0e-12
+# Tolerance the GPU parity tests apply.  0 = bit-exact, which the shipped (strict) kernels meet;
+# MXADV_TEST_TOL=1e-12 is for A/B runs of tolerance-mode builds (FMA contraction on).
+import os as _os
+STRICT_TOL = float(_os.environ.get("MXADV_TEST_TOL", "0.0"))
+assert STRICT_TOL <= REL_TOL
 
 
 def max_rel_err(a: np.ndarray, ref: np.ndarray) -> float:

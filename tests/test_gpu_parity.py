@@ -11,8 +11,7 @@ from test_oracle_vs_reference import CASES_3D
 
 pytestmark = pytest.mark.gpu
 
-TOL = 0.0  # bit-exact; REL_TOL (1e-12) is the contractual bound
-assert TOL <= REL_TOL
+from common import STRICT_TOL as TOL  # 0 unless MXADV_TEST_TOL is set
 
 
 @pytest.fixture(scope="module")
@@ -185,20 +184,17 @@ def test_fused_density_pass(mx, oracle_calls, ppm, bck, spt, nspec, n, residency
 
 
 @pytest.mark.parametrize("residency", ["host", "device"])
-@pytest.mark.parametrize("ppm,spt,nspec,n,kernel", [
-    (1, 1, 3, (37, 19, 23), None),
-    (0, 1, 13, (33, 33, 12), None),
-    (2, 3, 4, (20, 18, 40), None),
-    (1, 1, 5, (31, 29, 35), "v5"),
+@pytest.mark.parametrize("ppm,spt,nspec,n", [
+    (1, 1, 3, (37, 19, 23)),
+    (0, 1, 13, (33, 33, 12)),
+    (2, 3, 4, (20, 18, 40)),
+    (1, 1, 5, (31, 29, 35)),
 ])
-def test_fused_density_pass_spherical(mx, oracle_calls, ppm, spt, nspec, n, kernel, residency,
-                                      monkeypatch):
+def test_fused_density_pass_spherical(mx, oracle_calls, ppm, spt, nspec, n, residency):
     """wdconvect-like: spherical flux form (r0mac face arrays, no etarhoflux), outflow BCs;
     the time-centred rho0 on faces is pre-averaged by the library (mac_average)."""
     from gpu_util import to_device, to_host
     from maestroex_b200.fusedcalls import density_edge_flux
-    if kernel:
-        monkeypatch.setenv("MXADV_KERNEL", kernel)
     ng = 4 if ppm == 2 else 3
     prob = make_problem(dim=3, n=n, nspec=nspec, ng=ng, bc_kind="outflow", seed=77, spherical=True)
     epar = prob.edge_params(FIRSTSPEC, nspec, ppm_type=ppm)

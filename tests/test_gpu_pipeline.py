@@ -11,7 +11,7 @@ from common import (FIRSTSPEC, RHO, RHOH, assert_same, compare_faces, make_probl
                     run_rhoh, run_rhoX)
 
 pytestmark = pytest.mark.gpu
-TOL = 0.0
+from common import STRICT_TOL as TOL  # 0 unless MXADV_TEST_TOL is set
 
 
 @pytest.fixture(scope="module")

@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Static instruction statistics of the plane loop of a streaming kernel (non-BC body = the last
-inner loop in the function).  usage: loopstat.py <lib.so> <kernel-substring> [nth-loop-from-end]"""
+"""Static instruction statistics of the loops of one kernel in libmxadv.so.
+usage: loopstat.py <lib.so> <kernel-substring> [-v] [--min N]
+Lists every loop (backward branch) with at least --min instructions (default 300): size, fp64-pipe
+count, selects, local-memory (spill) accesses, barriers; -v adds the opcode histogram."""
 import collections, re, subprocess, sys, tempfile, os, glob
 so, key = sys.argv[1], sys.argv[2]
-nth = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+minlen = int(sys.argv[sys.argv.index('--min') + 1]) if '--min' in sys.argv else 300
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
 cub = [c for c in glob.glob(d + "/*.cubin") if "fused" in c][0]
@@ -15,28 +17,26 @@ for l in sass.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
     if m:
         ins.append((int(m.group(1), 16), m.group(2).strip()))
-back = []
+def opof(t):
+    p = t.split()
+    return p[1] if p[0].startswith('@') else p[0]
+loops = []
 for a, t in ins:
     m = re.search(r"\bBRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", t)
     if m and int(m.group(1), 16) < a:
-        back.append((a, int(m.group(1), 16)))
-back.sort(reverse=True)
-# inner plane loops: backward branches spanning > 0x2000 bytes, innermost = smallest span containing 5 BAR
-loops = []
-for a, tgt in back:
-    body = [t for (x, t) in ins if tgt <= x <= a]
-    nbar = sum(1 for t in body if t.split()[-2 if t.startswith('@') else 0].startswith('BAR') or 'BAR.SYNC' in t)
-    if nbar == 5:
-        loops.append((a, tgt, body))
-a, tgt, body = loops[nth]
-ops = collections.Counter()
-for t in body:
-    p = t.split()
-    op = p[1] if p[0].startswith('@') else p[0]
-    ops[op] += 1
-tot = len(body)
-f64 = sum(v for k, v in ops.items() if k.startswith(('DADD', 'DMUL', 'DFMA', 'DSETP')))
-print(f"{fn[-40:]}: loop 0x{tgt:x}..0x{a:x}: {tot} instr, fp64 {f64}, FSEL {ops['FSEL']}, other {tot - f64 - ops['FSEL']}")
-if '-v' in sys.argv:
-    for k, v in ops.most_common(40):
-        print(f"   {k:24s}{v}")
+        tgt = int(m.group(1), 16)
+        body = [x for x in ins if tgt <= x[0] <= a]
+        if len(body) >= minlen:
+            loops.append((tgt, a, body))
+print(f"{fn[-46:]}: {len(ins)} instructions")
+for tgt, a, body in sorted(loops):
+    ops = collections.Counter(opof(t) for _, t in body)
+    f64 = sum(v for k, v in ops.items() if k.startswith(('DADD', 'DMUL', 'DFMA', 'DSETP')))
+    sel = sum(v for k, v in ops.items() if k.startswith(('FSEL', 'SEL')))
+    loc = sum(v for k, v in ops.items() if k.startswith(('LDL', 'STL')))
+    bar = sum(v for k, v in ops.items() if k.startswith('BAR'))
+    sm = sum(v for k, v in ops.items() if k.startswith(('LDS', 'STS')))
+    print(f"  loop 0x{tgt:x}..0x{a:x}: {len(body)} instr, fp64 {f64}, sel {sel}, lds/sts {sm}, local {loc}, bar {bar}")
+    if '-v' in sys.argv:
+        for k, v in ops.most_common(28):
+            print(f"       {k:24s}{v}")
