@@ -132,16 +132,21 @@ def cpu_backend():
 
 
 def cpu_step(calls, prob, ppm, spherical=False):
-    """density pass + enthalpy pass with the separate reference member functions."""
-    from common import run_edge, run_rhoh, run_rhoX
+    """density pass + enthalpy pass with the separate reference member functions, writing into
+    the problem's own output fabs (no harness copies inside the timed region)."""
+    from common import run_edge, run_rhoh
     from maestroex_b200.synth import FIRSTSPEC, RHO, RHOH
-    sedge = run_edge(calls, prob, prob.edge_params(FIRSTSPEC, prob.nspec, ppm_type=ppm),
-                     sedge=prob.sedge)
+    sedge, sflux, eta = prob.sedge, prob.sflux, prob.etarhoflux
+    run_edge(calls, prob, prob.edge_params(FIRSTSPEC, prob.nspec, ppm_type=ppm), sedge=sedge)
     run_edge(calls, prob, prob.edge_params(RHO, 1, ppm_type=ppm), sedge=sedge)
     fpar = prob.flux_params(spherical=1 if spherical else 0)
-    run_rhoX(calls, prob, sedge, fpar)
+    b = prob.base
+    calls.make_rhoX_flux(prob.geom, sflux, eta, sedge, prob.umac, b["rho0_old"],
+                         b["rho0_edge_old"], prob.mac.get("r0mac_old"), b["rho0_new"],
+                         b["rho0_edge_new"], prob.mac.get("r0mac_new"),
+                         b["rho0_predicted_edge"], b["w0"], fpar)
     run_edge(calls, prob, prob.edge_params(RHOH, 1, ppm_type=ppm), sedge=sedge)
-    run_rhoh(calls, prob, sedge, fpar)
+    run_rhoh(calls, prob, sedge, fpar, sflux=sflux)
 
 
 def cpu_measure(a, steps, warmup):
