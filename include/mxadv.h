@@ -312,6 +312,35 @@ int mx_halo_unpack(const MxGeom* geom, const MxFab* fab, int dir, int side, int 
 /* Number of doubles mx_halo_pack writes for these arguments. */
 long long mx_halo_count(const MxGeom* geom, const MxFab* fab, int dir, int ng, int ncomp);
 
+/* ---- multi-GPU: the bricks of one level, one per GPU ---------------
+ * mx_halo_exchange fills the `ng` ghost layers of components [comp0, comp0+ncomp) of this
+ * rank's fab from its face neighbours in a px*py*pz brick grid (x fastest, AMReX box order),
+ * direction by direction so that edge and corner ghosts are carried along: what
+ * FabArray::FillBoundary does for this path (external/amrex/Src/Base/AMReX_FabArrayCommI.H:8-150;
+ * reached from Source/MaestroDensityAdvance.cpp:98-104 / MaestroEnthalpyAdvance.cpp:120-136
+ * through FillPatch).  Directions with a single brick are left to the caller (periodic image
+ * of the brick itself or physical BC).  periodic[d] != 0: wrap around in direction d;
+ * otherwise the bricks on the domain faces have no neighbour there.  Asynchronous on `stream`.
+ *
+ * One rank per GPU: processes (MPI, torchrun) or host threads of one process.  Rank 0 calls
+ * mx_comm_unique_id and hands the 128 bytes to every rank by its own means (MPI_Bcast,
+ * torch.distributed, a file); every rank then calls mx_comm_create with its device current.
+ * Transports: MX_HALO_NCCL = packed slabs by ncclSend/ncclRecv; MX_HALO_P2P = the sender's pack
+ * kernel stores directly into the receiver's slab buffer over NVLink (CUDA IPC / peer access),
+ * completion by device-side epoch flags, no host synchronisation. */
+typedef struct MxComm MxComm;
+#define MX_COMM_ID_BYTES 128
+#define MX_HALO_NCCL 0
+#define MX_HALO_P2P 1
+int mx_comm_unique_id(unsigned char id[MX_COMM_ID_BYTES]);
+int mx_comm_create(MxComm** comm, const unsigned char id[MX_COMM_ID_BYTES], int rank, int nranks,
+                   const int grid[3], int transport);
+int mx_comm_destroy(MxComm* comm);
+int mx_halo_exchange(MxComm* comm, const MxGeom* geom, const MxFab* fab, int ng, int comp0,
+                     int ncomp, const int periodic[3], void* stream);
+/* bytes this rank sent during its last mx_halo_exchange */
+long long mx_comm_bytes_sent(const MxComm* comm);
+
 #ifdef __cplusplus
 }
 #endif

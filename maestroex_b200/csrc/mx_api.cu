@@ -526,6 +526,15 @@ int need_base(const MxBase* b, const char* name) {
 
 }  // namespace
 
+int mx_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
 void mx_count_launch(int n) { g_launches += n; }
 void mx_count_tma_launch() { g_tma_launches += 1; }
 

@@ -78,6 +78,8 @@ struct KFlux {
     int st_rhoh0_old, st_rhoh0_new, st_rhoh0_edge_old, st_rhoh0_edge_new;
 };
 
+// sets mx_last_error() of the calling thread and returns `code` (mx_api.cu)
+int mx_fail(int code, const char* fmt, ...);
 void mx_count_launch(int n = 1);
 void mx_count_tma_launch();
 

@@ -243,12 +243,15 @@ void cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi,
 
 void halo_pack(const KGeom& g, const DFab& fab, int dir, int side, int ng, int comp0, int ncomp,
                double* buf, bool unpack, cudaStream_t stream) {
-    // index (relative to the fab's low corner) of the first plane of the slab
+    // index (relative to the fab's low corner) of the first plane of the slab.  A fab that is
+    // nodal in `dir` (a MAC velocity / edge array: n+1 faces over n cells) shares its outermost
+    // valid face with the neighbour, so the interior slab starts one face further in.
     const int nghost = g.vlo[dir] - fab.lo[dir];
+    const int nodal = (fab.n[dir] - (g.vhi[dir] - g.vlo[dir] + 1)) & 1;
     int start;
     if (!unpack) {
         // interior cells adjacent to the face: what the neighbour's ghost region needs
-        start = side == 0 ? nghost : fab.n[dir] - nghost - ng;
+        start = side == 0 ? nghost + nodal : fab.n[dir] - nghost - ng - nodal;
     } else {
         start = side == 0 ? nghost - ng : fab.n[dir] - nghost;
     }

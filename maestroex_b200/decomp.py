@@ -194,3 +194,47 @@ class HaloExchanger:
                 pk.unpack(self.geom, self.fab, d, side, self.ng, c0, nc, rb, stream)
         self.bytes_sent_last = sent
         return sent
+
+
+class LibExchanger:
+    """The product path: mx_halo_exchange of libmxadv.so (include/mxadv.h) — brick topology,
+    packing, transport (NCCL send/recv or NVLink peer stores) and unpacking all happen behind
+    the C ABI; Python only hands the 128-byte communicator id from rank 0 to the other ranks
+    (torch.distributed broadcast; a C++ host would use MPI_Bcast)."""
+
+    NCCL, P2P = 0, 1
+
+    def __init__(self, calls, rank: int, world: int, grid, transport: int = 0, dist=None,
+                 device=None):
+        import torch
+        self.calls, self.lib = calls, calls.lib
+        self.rank, self.world, self.grid = rank, world, tuple(int(x) for x in grid)
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            calls._check(self.lib.mx_comm_unique_id(idbuf), "comm_unique_id")
+        if world > 1:
+            if dist is None:
+                import torch.distributed as dist  # noqa: PLC0415
+            t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8,
+                             device=device if device is not None else "cpu")
+            dist.broadcast(t, src=0)
+            idbuf = (C.c_ubyte * 128)(*[int(x) for x in t.cpu().tolist()])
+        self.comm = C.c_void_p()
+        g = (C.c_int * 3)(*self.grid)
+        calls._check(self.lib.mx_comm_create(C.byref(self.comm), idbuf, rank, world, g,
+                                             int(transport)), "comm_create")
+        self.lib.mx_comm_bytes_sent.restype = C.c_longlong
+        self.lib.mx_comm_bytes_sent.argtypes = [C.c_void_p]
+
+    def exchange(self, geom, fab, ng: int, comp0: int, ncomp: int, periodic, stream: int = 0):
+        g, f = geom.c(), fab.c()
+        per = (C.c_int * 3)(*[1 if p else 0 for p in periodic])
+        rc = self.lib.mx_halo_exchange(self.comm, C.byref(g), C.byref(f), int(ng), int(comp0),
+                                       int(ncomp), per, C.c_void_p(stream))
+        self.calls._check(rc, "halo_exchange")
+        return int(self.lib.mx_comm_bytes_sent(self.comm))
+
+    def close(self):
+        if self.comm:
+            self.lib.mx_comm_destroy(self.comm)
+            self.comm = C.c_void_p()
