@@ -446,6 +446,9 @@ MXD double upw(bool pos, bool nz, bool slow, double sl, double sr) {
     return r;
 }
 
+// the stagnation arm of the Riemann choice on its own: `r` is the upwind state already chosen
+MXD double upw_avg(bool nz, double r, double sl, double sr) { return nz ? r : 0.5 * (sl + sr); }
+
 // :710-742 and the identical blocks in the transverse stage
 MXD void bc_pair(int I, int lo, int hi, int bclo, int bchi, bool velclamp, double s_lo,
                  double s_hi, double& sl, double& sr) {

@@ -30,6 +30,8 @@
 #ifndef MX_STREAM6_CUH
 #define MX_STREAM6_CUH
 
+#include <type_traits>
+
 constexpr int S6_RS = 8;          // scalar ring slots
 constexpr int S6_IS = 3;          // I-buffer slots
 constexpr int S6_IBS = 17 * 32;   // doubles per I-buffer array: 16 tile rows + one slack row
@@ -533,216 +535,231 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                 0xffffffffu, !(px_nz0 && px_nz && py_nz0 && py_nz && pz_nz0 && pz_nz && py2_nz0));
             const bool slow = slow_c || slow_p;
 
+            // Two copies of the plane body, chosen per warp and plane: the common one has no
+            // stagnation arm at all (upwinding = one select); the other also averages where |u|
+            // is below the threshold (MaestroMakeEdgeScalars.cpp:745-748).  Both contain the same
+            // barrier sequence, so warps of one block may take different copies.
+            auto plane = [&](auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
             // ---- P2: 1-D states from the I-buffer, first Riemann solve -----------------------
-            bar_sync(B6_FULL + it % 3, S6_NT);  // plane a has been reconstructed
-            const double* const I = ibuf + (it % 3) * 6 * S6_IBS + tid;
-            const double* const Ip_ = ibuf + ((it + 2) % 3) * 6 * S6_IBS + tid;  // plane a-1
-            double slx = I[0 * S6_IBS], srx = I[1 * S6_IBS];
-            double sly = I[2 * S6_IBS], sry = I[3 * S6_IBS];
-            double slz = I[4 * S6_IBS], srz = I[5 * S6_IBS];
-            if (BC) {
-                if (bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, slx, srx);
-                if (bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, sly, sry);
-                if (bcz) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, slz, srz);
-            }
-            const double shx = upw(px_pos, px_nz0, slow, slx, srx);  // QUIRK: |u| > 0.0 (:746)
-            const double shy = upw(py_pos, py_nz0, slow, sly, sry);
-            const double shz = upw(pz_pos, pz_nz0, slow, slz, srz);
-            double shy_up;  // first Riemann solve of my HIGH y face (the row above's low face)
-            {
-                double l = I[2 * S6_IBS + GX], r = I[3 * S6_IBS + GX];
-                if (BC && bcy) bc_pair(j + 1, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
-                shy_up = upw(py2_pos, py2_nz0, slow, l, r);
-            }
-
-            // ---- P3: transverse differences (dt/6 form) --------------------------------------
-            const double usx = up + um, usy = vp + vm;
-            const double t6x = (c6x * usx) * (shfl_dn1(shx) - shx);
-            const double t6y = (c6y * usy) * (shy_up - shy);
-            const double wsum_p = w_0 + w_m1;
-            const double tz = (c6z * wsum_p) * (shz - HS(H_SHZ));
-            HS(H_SHZ) = shz;
-            X_T6X[tid] = t6x;
-            X_TZ[tid] = tz;
-            const bool do_xy = a > k0;
-            const bool do_z = a >= k0 && (a < k1 || last);
-            double r_x = 0.0, r_y = 0.0, r_z = 0.0, g_x = 0.0, g_y = 0.0, g_z = 0.0, e_z = 0.0;
-            double q_x = 0.0, q_y = 0.0, q_z = 0.0;
-            if ((MODE == 1 && flux1) || MODE == 2) {
-                if (need_ser) {
-                    if (do_xy) {
-                        r_x = pEx[dRx];
-                        r_y = pEy[dRy];
-                    }
-                    if (do_z) r_z = pEz[dRz];
+                bar_sync(B6_FULL + it % 3, S6_NT);  // plane a has been reconstructed
+                const double* const I = ibuf + (it % 3) * 6 * S6_IBS + tid;
+                const double* const Ip_ = ibuf + ((it + 2) % 3) * 6 * S6_IBS + tid;  // plane a-1
+                double slx = I[0 * S6_IBS], srx = I[1 * S6_IBS];
+                double sly = I[2 * S6_IBS], sry = I[3 * S6_IBS];
+                double slz = I[4 * S6_IBS], srz = I[5 * S6_IBS];
+                if (BC) {
+                    if (bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, slx, srx);
+                    if (bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, sly, sry);
+                    if (bcz) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, slz, srz);
                 }
-                if (MODE == 1 && !first_spec) {
-                    if (do_xy) {
-                        g_x = pFx[dGx];
-                        g_y = pFy[dGy];
-                    }
-                    if (do_z) g_z = pFz[dGz];
-                }
-                if (MODE == 1 && A.do_eta && do_z) e_z = pEta[0];
-                if (MODE == 1 && sph) {
-                    if (do_xy) {
-                        q_x = pEx[dQx];
-                        q_y = pEy[dQy];
-                    }
-                    if (do_z) q_z = pEz[dQz];
-                }
-            }
-            bar_sync(B6_Q1, S6_NQ);  // S4
-
-            // ---- P4: corner-coupled states ---------------------------------------------------
-            const double uf_p = HS(H_UF), vf_p = HS(H_VF);
-            const bool qx_pos = uf_p > 0.0, qx_nz = fabs(uf_p) > eps;
-            const bool qy_pos = vf_p > 0.0, qy_nz = fabs(vf_p) > eps;
-            double slx_p = Ip_[0 * S6_IBS], srx_p = Ip_[1 * S6_IBS];
-            double sly_p = Ip_[2 * S6_IBS], sry_p = Ip_[3 * S6_IBS];
-            if (BC) {  // the plane below went through the same boundary overrides
-                if (bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, slx_p, srx_p);
-                if (bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, sly_p, sry_p);
-            }
-            double hxy, hyx, hzx, hzy, hxz, hyz;
-            {
-                double l = slx - shfl_up1(t6y), r = srx - t6y;
-                if (BC && bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, l, r);
-                hxy = upw(px_pos, px_nz, slow, l, r);
-                l = sly - X_T6X[tid - GX];
-                r = sry - t6x;
-                if (BC && bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
-                hyx = upw(py_pos, py_nz, slow, l, r);
-                l = slz - HS(H_T6X);
-                r = srz - t6x;
-                if (BC && bcz) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, l, r);
-                hzx = upw(pz_pos, pz_nz, slow, l, r);
-                l = slz - HS(H_T6Y);
-                r = srz - t6y;
-                if (BC && bcz) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, l, r);
-                hzy = upw(pz_pos, pz_nz, slow, l, r);
-                l = slx_p - shfl_up1(tz);
-                r = srx_p - tz;
-                if (BC && bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, l, r);
-                hxz = upw(qx_pos, qx_nz, slow, l, r);
-                l = sly_p - X_TZ[tid - GX];
-                r = sry_p - tz;
-                if (BC && bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
-                hyz = upw(qy_pos, qy_nz, slow, l, r);
-            }
-            HS(H_T6X) = t6x;
-            HS(H_T6Y) = t6y;
-            X_HYX[tid] = hyx;
-            X_HYZ[tid] = hyz;
-            const double c4zw = c4z * wsum_p;
-            const double t4xz = HS(H_C4X) * (shfl_dn1(hxz) - hxz);
-            const double t4zx = c4zw * (hzx - HS(H_HZX));
-            const double fs_prev = HS(H_FS);
-            X_QY1[tid] = t4xz;
-            X_QY2[tid] = t4zx;
-            X_FS[tid] = fs_prev;
-            bar_sync(B6_Q2, S6_NQ);  // S5
-
-            // ---- P5: transverse differences (dt/4 form) --------------------------------------
-            const double c4xu = c4x * usx, c4yu = c4y * usy;
-            const double t4xy = c4xu * (shfl_dn1(hxy) - hxy);
-            const double t4yx = c4yu * (X_HYX[tid + GX] - hyx);
-            const double t4yz = HS(H_C4Y) * (X_HYZ[tid + GX] - hyz);
-            const double t4zy = c4zw * (hzy - HS(H_HZY));
-            const double fs_cur = A.dt2 * f0;
-
-            // ---- P6: final edge states (+ fluxes) --------------------------------------------
-            if (do_xy) {
-                double ex_v, ey_v;
+                const double shx = upw(px_pos, px_nz0, SLOW, slx, srx);  // QUIRK: |u| > 0.0 (:746)
+                const double shy = upw(py_pos, py_nz0, SLOW, sly, sry);
+                const double shz = upw(pz_pos, pz_nz0, SLOW, slz, srz);
+                double shy_up;  // first Riemann solve of my HIGH y face (the row above's low face)
                 {
-                    const double el = ((slx_p - shfl_up1(t4yz)) - shfl_up1(t4zy)) + shfl_up1(fs_prev);
-                    const double er = ((srx_p - t4yz) - t4zy) + fs_prev;
-                    ex_v = upw(qx_pos, qx_nz, slow, el, er);
-                    if (BC && bcx) ex_v = bc_final(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, el, er, ex_v);
+                    double l = I[2 * S6_IBS + GX], r = I[3 * S6_IBS + GX];
+                    if (BC && bcy) bc_pair(j + 1, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
+                    shy_up = upw(py2_pos, py2_nz0, SLOW, l, r);
                 }
+
+                // ---- P3: transverse differences (dt/6 form) --------------------------------------
+                const double usx = up + um, usy = vp + vm;
+                const double t6x = (c6x * usx) * (shfl_dn1(shx) - shx);
+                const double t6y = (c6y * usy) * (shy_up - shy);
+                const double wsum_p = w_0 + w_m1;
+                const double tz = (c6z * wsum_p) * (shz - HS(H_SHZ));
+                HS(H_SHZ) = shz;
+                X_T6X[tid] = t6x;
+                X_TZ[tid] = tz;
+                const bool do_xy = a > k0;
+                const bool do_z = a >= k0 && (a < k1 || last);
+                double r_x = 0.0, r_y = 0.0, r_z = 0.0, g_x = 0.0, g_y = 0.0, g_z = 0.0, e_z = 0.0;
+                double q_x = 0.0, q_y = 0.0, q_z = 0.0;
+                if ((MODE == 1 && flux1) || MODE == 2) {
+                    if (need_ser) {
+                        if (do_xy) {
+                            r_x = pEx[dRx];
+                            r_y = pEy[dRy];
+                        }
+                        if (do_z) r_z = pEz[dRz];
+                    }
+                    if (MODE == 1 && !first_spec) {
+                        if (do_xy) {
+                            g_x = pFx[dGx];
+                            g_y = pFy[dGy];
+                        }
+                        if (do_z) g_z = pFz[dGz];
+                    }
+                    if (MODE == 1 && A.do_eta && do_z) e_z = pEta[0];
+                    if (MODE == 1 && sph) {
+                        if (do_xy) {
+                            q_x = pEx[dQx];
+                            q_y = pEy[dQy];
+                        }
+                        if (do_z) q_z = pEz[dQz];
+                    }
+                }
+                bar_sync(B6_Q1, S6_NQ);  // S4
+
+                // ---- P4: corner-coupled states ---------------------------------------------------
+                const double uf_p = HS(H_UF), vf_p = HS(H_VF);
+                const bool qx_pos = uf_p > 0.0, qx_nz = fabs(uf_p) > eps;
+                const bool qy_pos = vf_p > 0.0, qy_nz = fabs(vf_p) > eps;
+                double slx_p = Ip_[0 * S6_IBS], srx_p = Ip_[1 * S6_IBS];
+                double sly_p = Ip_[2 * S6_IBS], sry_p = Ip_[3 * S6_IBS];
+                if (BC) {  // the plane below went through the same boundary overrides
+                    if (bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, slx_p, srx_p);
+                    if (bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, sly_p, sry_p);
+                }
+                double hxy, hyx, hzx, hzy, hxz, hyz;
                 {
-                    const double el = ((sly_p - X_QY1[tid - GX]) - X_QY2[tid - GX]) + X_FS[tid - GX];
-                    const double er = ((sry_p - t4xz) - t4zx) + fs_prev;
-                    ey_v = upw(qy_pos, qy_nz, slow, el, er);
-                    if (BC && bcy) ey_v = bc_final(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, el, er, ey_v);
+                    double l = slx - shfl_up1(t6y), r = srx - t6y;
+                    if (BC && bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, l, r);
+                    hxy = upw(px_pos, px_nz, SLOW, l, r);
+                    l = sly - X_T6X[tid - GX];
+                    r = sry - t6x;
+                    if (BC && bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
+                    hyx = upw(py_pos, py_nz, SLOW, l, r);
+                    l = slz - HS(H_T6X);
+                    r = srz - t6x;
+                    if (BC && bcz) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, l, r);
+                    hzx = upw(pz_pos, pz_nz, SLOW, l, r);
+                    l = slz - HS(H_T6Y);
+                    r = srz - t6y;
+                    if (BC && bcz) bc_pair(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, l, r);
+                    hzy = upw(pz_pos, pz_nz, SLOW, l, r);
+                    l = slx_p - shfl_up1(tz);
+                    r = srx_p - tz;
+                    if (BC && bcx) bc_pair(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, l, r);
+                    hxz = upw(qx_pos, qx_nz, SLOW, l, r);
+                    l = sly_p - X_TZ[tid - GX];
+                    r = sry_p - tz;
+                    if (BC && bcy) bc_pair(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, l, r);
+                    hyz = upw(qy_pos, qy_nz, SLOW, l, r);
                 }
-                if (ownx) pEx[0] = ex_v;
-                if (owny) pEy[0] = ey_v;
-                if (MODE == 1 && flux1) {
-                    double r0x, r0y;
-                    if (sph) {
-                        r0x = q_x;
-                        r0y = q_y;
-                    } else {
-                        r0x = r0y = T_RXY[it - 1];
+                HS(H_T6X) = t6x;
+                HS(H_T6Y) = t6y;
+                X_HYX[tid] = hyx;
+                X_HYZ[tid] = hyz;
+                const double c4zw = c4z * wsum_p;
+                const double t4xz = HS(H_C4X) * (shfl_dn1(hxz) - hxz);
+                const double t4zx = c4zw * (hzx - HS(H_HZX));
+                const double fs_prev = HS(H_FS);
+                X_QY1[tid] = t4xz;
+                X_QY2[tid] = t4zx;
+                X_FS[tid] = fs_prev;
+                bar_sync(B6_Q2, S6_NQ);  // S5
+
+                // ---- P5: transverse differences (dt/4 form) --------------------------------------
+                const double c4xu = c4x * usx, c4yu = c4y * usy;
+                const double t4xy = c4xu * (shfl_dn1(hxy) - hxy);
+                const double t4yx = c4yu * (X_HYX[tid + GX] - hyx);
+                const double t4yz = HS(H_C4Y) * (X_HYZ[tid + GX] - hyz);
+                const double t4zy = c4zw * (hzy - HS(H_HZY));
+                const double fs_cur = A.dt2 * f0;
+
+                // ---- P6: final edge states (+ fluxes) --------------------------------------------
+                if (do_xy) {
+                    double ex_v, ey_v;
+                    {
+                        const double el = ((slx_p - shfl_up1(t4yz)) - shfl_up1(t4zy)) + shfl_up1(fs_prev);
+                        const double er = ((srx_p - t4yz) - t4zy) + fs_prev;
+                        ex_v = upw(qx_pos, qx_nz, SLOW, el, er);
+                        if (BC && bcx) ex_v = bc_final(i, g.dlo[0], g.dhi[0], bclx, bchx, vcx, 0.0, 0.0, el, er, ex_v);
                     }
-                    const double flx = rhoX_flux(F_.spt, uf_p, r0x, r_x, ex_v);
-                    const double fly = rhoX_flux(F_.spt, vf_p, r0y, r_y, ey_v);
-                    if (ownx) {
-                        pFx[0] = flx;
-                        pFx[dGx] = g_x + flx;
+                    {
+                        const double el = ((sly_p - X_QY1[tid - GX]) - X_QY2[tid - GX]) + X_FS[tid - GX];
+                        const double er = ((sry_p - t4xz) - t4zx) + fs_prev;
+                        ey_v = upw(qy_pos, qy_nz, SLOW, el, er);
+                        if (BC && bcy) ey_v = bc_final(j, g.dlo[1], g.dhi[1], bcly, bchy, vcy, 0.0, 0.0, el, er, ey_v);
                     }
-                    if (owny) {
-                        pFy[0] = fly;
-                        pFy[dGy] = g_y + fly;
+                    if (ownx) pEx[0] = ex_v;
+                    if (owny) pEy[0] = ey_v;
+                    if (MODE == 1 && flux1) {
+                        double r0x, r0y;
+                        if (sph) {
+                            r0x = q_x;
+                            r0y = q_y;
+                        } else {
+                            r0x = r0y = T_RXY[it - 1];
+                        }
+                        const double flx = rhoX_flux(F_.spt, uf_p, r0x, r_x, ex_v);
+                        const double fly = rhoX_flux(F_.spt, vf_p, r0y, r_y, ey_v);
+                        if (ownx) {
+                            pFx[0] = flx;
+                            pFx[dGx] = g_x + flx;
+                        }
+                        if (owny) {
+                            pFy[0] = fly;
+                            pFy[dGy] = g_y + fly;
+                        }
+                    } else if (MODE == 2) {
+                        double fl;
+                        if (rhoh_flux_tab(F_, have_h, uf_p, r_x, ex_v, T_RXY[it - 1], T_HXY[it - 1], false, &fl))
+                            if (ownx) pFx[0] = fl;
+                        if (rhoh_flux_tab(F_, have_h, vf_p, r_y, ey_v, T_RXY[it - 1], T_HXY[it - 1], false, &fl))
+                            if (owny) pFy[0] = fl;
                     }
-                } else if (MODE == 2) {
-                    double fl;
-                    if (rhoh_flux_tab(F_, have_h, uf_p, r_x, ex_v, T_RXY[it - 1], T_HXY[it - 1], false, &fl))
-                        if (ownx) pFx[0] = fl;
-                    if (rhoh_flux_tab(F_, have_h, vf_p, r_y, ey_v, T_RXY[it - 1], T_HXY[it - 1], false, &fl))
-                        if (owny) pFy[0] = fl;
                 }
-            }
-            const double el_z = ((slz - HS(H_T4XY)) - HS(H_T4YX)) + fs_prev;
-            const double er_z = ((srz - t4xy) - t4yx) + fs_cur;
-            if (do_z) {
-                double ez_v = upw(pz_pos, pz_nz, slow, el_z, er_z);
-                if (BC && bcz) ez_v = bc_final(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, el_z, er_z, ez_v);
-                if (ownz) pEz[0] = ez_v;
-                if (MODE == 1 && flux1) {
-                    double r0z;
-                    if (sph) {
-                        r0z = q_z;
-                    } else {
-                        r0z = T_RZ[it];
+                const double el_z = ((slz - HS(H_T4XY)) - HS(H_T4YX)) + fs_prev;
+                const double er_z = ((srz - t4xy) - t4yx) + fs_cur;
+                if (do_z) {
+                    double ez_v = upw(pz_pos, pz_nz, SLOW, el_z, er_z);
+                    if (BC && bcz) ez_v = bc_final(a, g.dlo[2], g.dhi[2], bclz, bchz, vcz, 0.0, 0.0, el_z, er_z, ez_v);
+                    if (ownz) pEz[0] = ez_v;
+                    if (MODE == 1 && flux1) {
+                        double r0z;
+                        if (sph) {
+                            r0z = q_z;
+                        } else {
+                            r0z = T_RZ[it];
+                        }
+                        const double flz = rhoX_flux(F_.spt, w_0, r0z, r_z, ez_v);
+                        if (ownz) {
+                            pFz[0] = flz;
+                            pFz[dGz] = g_z + flz;
+                        }
+                        if (A.do_eta) {
+                            double ev = e_z;
+                            if (is_spec) ev += flz;
+                            if (last_spec) ev -= T_W0R[it];
+                            if (ownz) pEta[0] = ev;
+                        }
+                    } else if (MODE == 2) {
+                        double fl;
+                        if (rhoh_flux_tab(F_, have_h, w_0, r_z, ez_v, T_RZ[it], T_HZ[it], true, &fl))
+                            if (ownz) pFz[0] = fl;
                     }
-                    const double flz = rhoX_flux(F_.spt, w_0, r0z, r_z, ez_v);
-                    if (ownz) {
-                        pFz[0] = flz;
-                        pFz[dGz] = g_z + flz;
-                    }
-                    if (A.do_eta) {
-                        double ev = e_z;
-                        if (is_spec) ev += flz;
-                        if (last_spec) ev -= T_W0R[it];
-                        if (ownz) pEta[0] = ev;
-                    }
-                } else if (MODE == 2) {
-                    double fl;
-                    if (rhoh_flux_tab(F_, have_h, w_0, r_z, ez_v, T_RZ[it], T_HZ[it], true, &fl))
-                        if (ownz) pFz[0] = fl;
                 }
-            }
-            pEx += ex_sz;
-            pEy += ey_sz;
-            pEz += ez_sz;
-            if (MODE != 0) {
-                pFx += fx_sz;
-                pFy += fy_sz;
-                pFz += fz_sz;
-                if (MODE == 1) pEta += eta_sz;
-            }
-            // ---- z history for the next plane; release the slot of plane a-1 --------------------
-            HS(H_UF) = um;
-            HS(H_VF) = vm;
-            HS(H_C4X) = c4xu;
-            HS(H_C4Y) = c4yu;
-            HS(H_HZX) = hzx;
-            HS(H_HZY) = hzy;
-            HS(H_T4XY) = t4xy;
-            HS(H_T4YX) = t4yx;
-            HS(H_FS) = fs_cur;
+                pEx += ex_sz;
+                pEy += ey_sz;
+                pEz += ez_sz;
+                if (MODE != 0) {
+                    pFx += fx_sz;
+                    pFy += fy_sz;
+                    pFz += fz_sz;
+                    if (MODE == 1) pEta += eta_sz;
+                }
+                // ---- z history for the next plane; release the slot of plane a-1 --------------------
+                HS(H_UF) = um;
+                HS(H_VF) = vm;
+                HS(H_C4X) = c4xu;
+                HS(H_C4Y) = c4yu;
+                HS(H_HZX) = hzx;
+                HS(H_HZY) = hzy;
+                HS(H_T4XY) = t4xy;
+                HS(H_T4YX) = t4yx;
+                HS(H_FS) = fs_cur;
+            };
+#ifdef MX_COUNT_FAST_PATH  // static instruction counting of the common copy only (tools/loopstat.py)
+            plane(std::false_type{});
+#else
+            if (slow)
+                plane(std::true_type{});
+            else
+                plane(std::false_type{});
+#endif
             slow_p = slow_c;
             if (a + 2 <= k1) bar_arrive(B6_EMPTY + (it + 2) % 3, S6_NT);
         }
@@ -806,6 +823,10 @@ __global__ void __launch_bounds__(S6_NT, 1) k_stream6(const __grid_constant__ Fu
     }
     // (the first __syncthreads of either role publishes all of the above)
 
+    // Register budgets.  The kernel is launched at 96 registers per thread (640 threads); the
+    // four Riemann warpgroups give 8 each back to the CTA pool, which is exactly what the one
+    // reconstruction warpgroup needs to grow to 128 (setmaxnreg.inc only draws on registers
+    // released by setmaxnreg.dec of the same CTA): 512 x 88 + 128 x 128 = 640 x 96.
     if (tid >= S6_NQ) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;\n");
         if (bc)
@@ -813,6 +834,7 @@ __global__ void __launch_bounds__(S6_NT, 1) k_stream6(const __grid_constant__ Fu
         else
             stream6_recon<PPM, false>(A, sm6);
     } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n");
         if (bc)
             stream6_riemann<true, MODE, SPH>(A, sm6, RD);
         else

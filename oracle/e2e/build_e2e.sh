@@ -15,9 +15,13 @@
 # (git-ignored; travels to the GPU box, where /root/reference does not exist).  Nothing is
 # copied from the reference into the repository history.
 #
-# usage: oracle/e2e/build_e2e.sh [2|3]        (default 2)
+# usage: oracle/e2e/build_e2e.sh [2|3] [reacting_bubble|wdconvect]       (default 2, reacting_bubble)
+# wdconvect (Exec/science/wdconvect, 3-D only): spherical base state, outflow on all six faces,
+# BASELINE config 3; executables are named Maestro3d.wd.{ref,mx,fx}.ex.
 set -euo pipefail
 DIM=${1:-2}
+PROB=${2:-reacting_bubble}
+if [ "$PROB" = wdconvect ]; then PDIR=Exec/science/wdconvect; TAGP=wd_; SUF=.wd; else PDIR=Exec/test_problems/reacting_bubble; TAGP=rb_; SUF=; fi
 REF=${MAESTROEX_REF:-/root/reference}
 REPO=$(cd "$(dirname "$0")/../.." && pwd)
 OUT=$REPO/oracle/_ref/e2e
@@ -27,17 +31,17 @@ MK="make -j$J MAESTROEX_HOME=$REF DIM=$DIM USE_MPI=FALSE USE_OMP=TRUE COMP=gnu"
 mkdir -p "$OUT" "$WORK"
 
 # 1. the unmodified reference
-if [ ! -d "$WORK/rb_ref$DIM" ]; then
-    cp -r "$REF/Exec/test_problems/reacting_bubble" "$WORK/rb_ref$DIM"
+if [ ! -d "$WORK/${TAGP}ref$DIM" ]; then
+    cp -r "$REF/$PDIR" "$WORK/${TAGP}ref$DIM"
 fi
-(cd "$WORK/rb_ref$DIM" && $MK > build.log 2>&1)
-cp "$WORK/rb_ref$DIM/Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.ref.ex"
+(cd "$WORK/${TAGP}ref$DIM" && $MK > build.log 2>&1)
+cp "$WORK/${TAGP}ref$DIM/Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d$SUF.ref.ex"
 
 # 2. the overlay build: start from the reference's object files, drop the shadowed ones
 make -C "$REPO/maestroex_b200/csrc" > /dev/null
-rm -rf "$WORK/rb_mx$DIM"
-cp -r "$WORK/rb_ref$DIM" "$WORK/rb_mx$DIM"
-cd "$WORK/rb_mx$DIM"
+rm -rf "$WORK/${TAGP}mx$DIM"
+cp -r "$WORK/${TAGP}ref$DIM" "$WORK/${TAGP}mx$DIM"
+cd "$WORK/${TAGP}mx$DIM"
 rm -f Maestro${DIM}d.gnu.OMP.ex
 for f in MaestroMakeEdgeScalars MaestroMakeFlux MaestroCelltoEdge MaestroMakew0 MaestroAdvection; do
     find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
@@ -61,14 +65,14 @@ assert inc in mk
 open("GNUmakefile", "w").write(mk.replace(inc, add + inc + tail))
 EOF
 $MK > build_mx.log 2>&1
-cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.mx.ex"
+cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d$SUF.mx.ex"
 
 # 2b. (3-D) the fused overlay on top: DensityAdvance / EnthalpyAdvance shadowed as well, so the
 #     run goes through mx_density_edge_flux / mx_enthalpy_edge_flux, the kernels bench.py times
 if [ "$DIM" = 3 ]; then
-    rm -rf "$WORK/rb_fx$DIM"
-    cp -r "$WORK/rb_mx$DIM" "$WORK/rb_fx$DIM"
-    cd "$WORK/rb_fx$DIM"
+    rm -rf "$WORK/${TAGP}fx$DIM"
+    cp -r "$WORK/${TAGP}mx$DIM" "$WORK/${TAGP}fx$DIM"
+    cd "$WORK/${TAGP}fx$DIM"
     rm -f Maestro${DIM}d.gnu.OMP.ex
     for f in MaestroDensityAdvance MaestroEnthalpyAdvance; do
         find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
@@ -85,7 +89,7 @@ assert key in mk
 open("GNUmakefile", "w").write(mk.replace(key, add + key))
 EOF2
     $MK > build_fx.log 2>&1
-    cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d.fx.ex"
+    cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d$SUF.fx.ex"
 fi
 
 # 3. fcompare
@@ -96,7 +100,12 @@ cp "$WORK/plotfile/fcompare.gnu.ex" "$OUT/fcompare${DIM}d.ex"
 
 # 4. run-time data of the problem (inputs, initial model, EOS table; the table is 60 MB of
 #    text, shipped gzipped)
-cp "$WORK/rb_ref$DIM"/inputs_${DIM}d_C "$WORK/rb_ref$DIM"/model.hse.cool.coulomb "$OUT/"
+if [ "$PROB" = wdconvect ]; then
+    cp "$WORK/${TAGP}ref$DIM"/inputs_files/inputs_3d_regression "$OUT/inputs_3d_wdconvect"
+    cp "$WORK/${TAGP}ref$DIM"/model_files/kepler_new_6.25e8.hybrid.hse.320 "$OUT/"
+else
+    cp "$WORK/${TAGP}ref$DIM"/inputs_${DIM}d_C "$WORK/${TAGP}ref$DIM"/model.hse.cool.coulomb "$OUT/"
+fi
 [ -f "$OUT/helm_table.dat.gz" ] || gzip -c "$REF/external/Microphysics/EOS/helmholtz/helm_table.dat" > "$OUT/helm_table.dat.gz"
 strip "$OUT"/*.ex
 ls -la "$OUT"

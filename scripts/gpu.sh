@@ -17,13 +17,19 @@ import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     r = d.get("roofline", {})
-    print(f"{sys.argv[2]:28s} value {d['value']:.4g} ms/step {d['ms_per_step']:.2f} density-launch {r.get('ms_per_launch')} frac {r.get('frac')} e2e {d.get('e2e', {}).get('value')}")
+    e2e = (d.get("e2e") or {}).get("value")
+    print(f"{sys.argv[2]:28s} value {d['value']:.4g} ms/step {d['ms_per_step']:.2f} density-launch {r.get('ms_per_launch'):.3f} frac {r.get('frac'):.4f} kernel {r.get('kernel')} e2e {e2e}")
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
 case $task in
   k6first)   # first contact of a new kernel: parity of the new kernel, then A/B timing
+    # a hung kernel must not eat the lease: one tiny launch with a short leash first
+    if ! timeout -k 5 150 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; then
+      echo "SMOKE FAILED OR HUNG (rc $?)"; tail -5 $out/smoke.log; exit 1
+    fi
+    tail -2 $out/smoke.log
     timeout -k 10 900 python -m pytest tests/test_gpu_stream6.py -x -q -m gpu 2>&1 | tail -15 | tee $out/pytest_stream6.log
     bench 256_v4 MXADV_KERNEL=v4 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
     bench 256_k6 X=1 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
