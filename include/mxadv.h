@@ -211,7 +211,7 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
 /* EnthalpyAdvance's MakeEdgeScal(pred_comp) + MakeRhoHFlux
  * (Source/MaestroEnthalpyAdvance.cpp:141-146,229,312) in one pass; epar sweeps the single
  * component RhoH (enthalpy_pred_type 0/1/2/5) and reads sedge(Rho) where the flux form needs
- * it.  3-D planar only. */
+ * it.  3-D, plane-parallel base state (spherical: mx_enthalpy_edge_flux_sph). */
 int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
                           const MxFab* sflux, const MxFab* umac, const MxFab* force,
                           const MxEdgeParams* epar, const MxBase* rho0_old,
@@ -220,6 +220,17 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
                           const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
                           const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
                           void* stream);
+
+/* The same for a spherical base state (wdconvect): the flux forms of
+ * Source/MaestroMakeFlux.cpp:788-1021 read the base state from face arrays (3 fabs each, as
+ * MakeRhoHFlux receives them): r0mac / h0mac when !use_exact_base_state, rh0mac otherwise; the
+ * 1-D BaseState arrays are not used.  use_exact_base_state composes the two separate kernels. */
+int mx_enthalpy_edge_flux_sph(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                              const MxFab* sflux, const MxFab* umac, const MxFab* force,
+                              const MxEdgeParams* epar, const MxFab* r0mac_old,
+                              const MxFab* r0mac_new, const MxFab* rh0mac_old,
+                              const MxFab* rh0mac_new, const MxFab* h0mac_old,
+                              const MxFab* h0mac_new, const MxFluxParams* fpar, void* stream);
 
 /* ---- Maestro::CelltoEdge -----------------------------------------------------------------
  * Replaces Maestro::CelltoEdge (Source/MaestroCelltoEdge.cpp:5-55) for one radial level with

@@ -823,20 +823,26 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
     return S.finish();
 }
 
-int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
-                          const MxFab* sflux, const MxFab* umac, const MxFab* force,
-                          const MxEdgeParams* epar, const MxBase* rho0_old,
-                          const MxBase* rho0_edge_old, const MxBase* rho0_new,
-                          const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
-                          const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
-                          const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
-                          void* stream) {
+static int enthalpy_edge_flux_impl(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                                   const MxFab* sflux, const MxFab* umac, const MxFab* force,
+                                   const MxEdgeParams* epar, const MxBase* rho0_old,
+                                   const MxBase* rho0_edge_old, const MxBase* rho0_new,
+                                   const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
+                                   const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+                                   const MxBase* rhoh0_edge_new, const MxFab* r0mac_old,
+                                   const MxFab* r0mac_new, const MxFab* rh0mac_old,
+                                   const MxFab* rh0mac_new, const MxFab* h0mac_old,
+                                   const MxFab* h0mac_new, const MxFluxParams* fpar,
+                                   void* stream) {
     MX_TRY(check_geom(geom));
     if (!state || !sedge || !sflux || !umac || !force || !fpar)
         return fail(MX_ERR_INVALID, "null argument");
     MX_TRY(check_edge_params(geom, epar));
-    if (geom->dim != 3 || fpar->spherical)
-        return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_edge_flux is 3-D planar only");
+    if (geom->dim != 3) return fail(MX_ERR_UNSUPPORTED, "the fused enthalpy pass is 3-D only");
+    const bool sph = fpar->spherical != 0;
+    if (sph && (fpar->use_exact_base_state ? (!rh0mac_old || !rh0mac_new)
+                                           : (!r0mac_old || !r0mac_new || !h0mac_old || !h0mac_new)))
+        return fail(MX_ERR_INVALID, "spherical enthalpy pass: base-state face arrays are required");
     if (epar->is_vel) return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_edge_flux: is_vel");
     if (epar->num_comp != 1 || epar->start_scomp != fpar->rhoh_comp)
         return fail(MX_ERR_INVALID, "mx_enthalpy_edge_flux sweeps the single component RhoH");
@@ -854,7 +860,7 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
                       rhoh0_old, rhoh0_edge_old, rhoh0_new, rhoh0_edge_new, &f));
     const KGeom kg = make_kgeom(geom);
     const KEdge e = make_kedge(epar);
-    if (fused_enthalpy_supported(kg, e, f) && !is_device_ptr(state->p) &&
+    if (!sph && fused_enthalpy_supported(kg, e, f) && !is_device_ptr(state->p) &&
         kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE") && !getenv("MXADV_KERNEL"))
         S.defer_copies();
     EdgeArgs a;
@@ -868,26 +874,81 @@ int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* s
                      true));
         MX_TRY(S.upload(&sedge[d], a.sedge[d], fpar->rho_comp, 1));
     }
+    if (sph) {
+        if (fpar->use_exact_base_state) {
+            MX_TRY(stage_mac(S, geom, rh0mac_old, mac.rh0_old, "rh0mac_old"));
+            MX_TRY(stage_mac(S, geom, rh0mac_new, mac.rh0_new, "rh0mac_new"));
+        } else {
+            MX_TRY(stage_mac(S, geom, r0mac_old, mac.r0_old, "r0mac_old"));
+            MX_TRY(stage_mac(S, geom, r0mac_new, mac.r0_new, "r0mac_new"));
+            MX_TRY(stage_mac(S, geom, h0mac_old, mac.h0_old, "h0mac_old"));
+            MX_TRY(stage_mac(S, geom, h0mac_new, mac.h0_new, "h0mac_new"));
+        }
+    }
     if (S.deferred()) {
         int rc1 = 0;
         MX_TRY(S.run_slabs(
             kg, (epar->ppm_type == 2 ? 4 : 3) + 1,
             [&](const KGeom& g) {
-                return fused_enthalpy(g, e, epar, f, a.state, a.sedge, sf, a.umac, a.force,
-                                      S.stream());
+                return fused_enthalpy(g, e, epar, f, a.state, a.sedge, sf, a.umac, a.force, nullptr,
+                                      nullptr, S.stream());
             },
             &rc1));
         if (rc1 == 0) return S.finish();
         MX_TRY(S.upload_rest());
     } else if (fused_enthalpy_supported(kg, e, f)) {
-        const int rc =
-            fused_enthalpy(kg, e, epar, f, a.state, a.sedge, sf, a.umac, a.force, S.stream());
+        // spherical: the time-centred rho0 and h0 on faces, formed once in sedge's layout
+        double *r0e[3] = {nullptr, nullptr, nullptr}, *h0e[3] = {nullptr, nullptr, nullptr};
+        if (sph) {
+            for (int d = 0; d < 3; ++d) {
+                void* p = nullptr;
+                CUDA_OK(S.alloc(&p, sizeof(double) * (size_t)a.sedge[d].sn));
+                r0e[d] = static_cast<double*>(p);
+                mac_average(kg, d, mac.r0_old[d], mac.r0_new[d], a.sedge[d], r0e[d], S.stream());
+                CUDA_OK(S.alloc(&p, sizeof(double) * (size_t)a.sedge[d].sn));
+                h0e[d] = static_cast<double*>(p);
+                mac_average(kg, d, mac.h0_old[d], mac.h0_new[d], a.sedge[d], h0e[d], S.stream());
+            }
+        }
+        const int rc = fused_enthalpy(kg, e, epar, f, a.state, a.sedge, sf, a.umac, a.force,
+                                      sph ? r0e : nullptr, sph ? h0e : nullptr, S.stream());
         if (rc == 0) return S.finish();
         if (rc < 0) return fail(MX_ERR_CUDA, "fused enthalpy kernel launch failed");
     }
     MX_TRY(run_edge(S, kg, epar, a));
     flux_rhoh(kg, f, sf, a.sedge, a.umac, mac, S.stream());
     return S.finish();
+}
+
+int mx_enthalpy_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                          const MxFab* sflux, const MxFab* umac, const MxFab* force,
+                          const MxEdgeParams* epar, const MxBase* rho0_old,
+                          const MxBase* rho0_edge_old, const MxBase* rho0_new,
+                          const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
+                          const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+                          const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
+                          void* stream) {
+    if (fpar && fpar->spherical)
+        return fail(MX_ERR_UNSUPPORTED,
+                    "mx_enthalpy_edge_flux is plane-parallel; spherical: mx_enthalpy_edge_flux_sph");
+    return enthalpy_edge_flux_impl(geom, state, sedge, sflux, umac, force, epar, rho0_old,
+                                   rho0_edge_old, rho0_new, rho0_edge_new, rhoh0_old,
+                                   rhoh0_edge_old, rhoh0_new, rhoh0_edge_new, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, nullptr, fpar, stream);
+}
+
+int mx_enthalpy_edge_flux_sph(const MxGeom* geom, const MxFab* state, const MxFab* sedge,
+                              const MxFab* sflux, const MxFab* umac, const MxFab* force,
+                              const MxEdgeParams* epar, const MxFab* r0mac_old,
+                              const MxFab* r0mac_new, const MxFab* rh0mac_old,
+                              const MxFab* rh0mac_new, const MxFab* h0mac_old,
+                              const MxFab* h0mac_new, const MxFluxParams* fpar, void* stream) {
+    if (fpar && !fpar->spherical)
+        return fail(MX_ERR_INVALID, "mx_enthalpy_edge_flux_sph needs fpar->spherical");
+    return enthalpy_edge_flux_impl(geom, state, sedge, sflux, umac, force, epar, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, r0mac_old,
+                                   r0mac_new, rh0mac_old, rh0mac_new, h0mac_old, h0mac_new, fpar,
+                                   stream);
 }
 
 int mx_cell_to_edge(const double* cell, double* edge, int nr, int r_lo, int r_hi, void* stream) {

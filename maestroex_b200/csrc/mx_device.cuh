@@ -29,11 +29,61 @@ constexpr int BC_HOEXTRAP = 4;
 MXD double dmin_(double a, double b) { return (b < a) ? b : a; }
 MXD double dmax_(double a, double b) { return (a < b) ? b : a; }
 
+// ---------------------------------------------------------------------------------------
+// Two independent values processed in lock step.  The reconstruction role of k_stream6 runs ONE
+// warp per SM sub-partition, so its speed is set by dependent-issue latency (8 cycles per fp64
+// operation); writing the arithmetic over pairs (two tile rows at once) puts a second,
+// independent instruction next to every instruction of the chain.  Every device function below
+// that the parabolic reconstruction uses is generic over T = double or D2: the pair version is
+// the scalar expression tree applied to both halves, hence bit-identical.
+// ---------------------------------------------------------------------------------------
+struct D2 {
+    double a, b;
+};
+struct B2 {
+    bool a, b;
+};
+MXD D2 d2(double a, double b) { return D2{a, b}; }
+MXD D2 d2(double a) { return D2{a, a}; }
+MXD D2 operator+(D2 x, D2 y) { return D2{x.a + y.a, x.b + y.b}; }
+MXD D2 operator-(D2 x, D2 y) { return D2{x.a - y.a, x.b - y.b}; }
+MXD D2 operator*(D2 x, D2 y) { return D2{x.a * y.a, x.b * y.b}; }
+MXD D2 operator-(D2 x) { return D2{-x.a, -x.b}; }
+MXD D2 operator*(double s, D2 x) { return D2{s * x.a, s * x.b}; }
+MXD D2 operator*(D2 x, double s) { return D2{x.a * s, x.b * s}; }
+MXD D2 operator+(double s, D2 x) { return D2{s + x.a, s + x.b}; }
+MXD D2 operator-(double s, D2 x) { return D2{s - x.a, s - x.b}; }
+MXD D2 operator+(D2 x, double s) { return D2{x.a + s, x.b + s}; }
+MXD D2 operator-(D2 x, double s) { return D2{x.a - s, x.b - s}; }
+MXD B2 operator<(D2 x, D2 y) { return B2{x.a < y.a, x.b < y.b}; }
+MXD B2 operator>(D2 x, D2 y) { return B2{x.a > y.a, x.b > y.b}; }
+MXD B2 operator<=(D2 x, D2 y) { return B2{x.a <= y.a, x.b <= y.b}; }
+MXD B2 operator>=(D2 x, D2 y) { return B2{x.a >= y.a, x.b >= y.b}; }
+MXD B2 operator<(D2 x, double y) { return B2{x.a < y, x.b < y}; }
+MXD B2 operator>(D2 x, double y) { return B2{x.a > y, x.b > y}; }
+MXD B2 operator<=(D2 x, double y) { return B2{x.a <= y, x.b <= y}; }
+MXD B2 operator>=(D2 x, double y) { return B2{x.a >= y, x.b >= y}; }
+MXD B2 operator!(B2 m) { return B2{!m.a, !m.b}; }
+MXD B2 operator&&(B2 m, B2 n) { return B2{m.a && n.a, m.b && n.b}; }
+// select
+MXD double sel(bool m, double x, double y) { return m ? x : y; }
+MXD D2 sel(B2 m, D2 x, D2 y) { return D2{m.a ? x.a : y.a, m.b ? x.b : y.b}; }
+MXD D2 sel(B2 m, double x, double y) { return D2{m.a ? x : y, m.b ? x : y}; }
+MXD D2 dmin_(D2 a, D2 b) { return D2{dmin_(a.a, b.a), dmin_(a.b, b.b)}; }
+MXD D2 dmax_(D2 a, D2 b) { return D2{dmax_(a.a, b.a), dmax_(a.b, b.b)}; }
+MXD D2 fma_(D2 x, D2 y, D2 z) { return D2{__fma_rn(x.a, y.a, z.a), __fma_rn(x.b, y.b, z.b)}; }
+MXD D2 fma_(double x, D2 y, D2 z) { return D2{__fma_rn(x, y.a, z.a), __fma_rn(x, y.b, z.b)}; }
+MXD D2 fma_(D2 x, double y, D2 z) { return D2{__fma_rn(x.a, y, z.a), __fma_rn(x.b, y, z.b)}; }
+MXD double fma_(double x, double y, double z) { return __fma_rn(x, y, z); }
+MXD double mul_(double x, double y) { return __dmul_rn(x, y); }
+MXD D2 mul_(D2 x, double y) { return D2{__dmul_rn(x.a, y), __dmul_rn(x.b, y)}; }
+
 // copysign(1.0, sgn) * mag for mag >= +0 (exact: +-1 * mag only flips the sign bit)
 MXD double signed_mag(double mag, double sgn) {
     return __hiloint2double((__double2hiint(mag) & 0x7fffffff) | (__double2hiint(sgn) & 0x80000000),
                             __double2loint(mag));
 }
+MXD D2 signed_mag(D2 mag, D2 sgn) { return D2{signed_mag(mag.a, sgn.a), signed_mag(mag.b, sgn.b)}; }
 MXD double sign1(double sgn) { return signed_mag(1.0, sgn); }
 
 // (prod > 0.0) ? r : +0.0 as a select.  Written in PTX because nvcc otherwise sinks the
@@ -48,15 +98,18 @@ MXD double sel_pos(double prod, double r) {
     return out;
 }
 
+MXD D2 sel_pos(D2 prod, D2 r) { return D2{sel_pos(prod.a, r.a), sel_pos(prod.b, r.b)}; }
+
 // Correctly rounded x / c for the compile-time constants c = 6 and c = 3 (Markstein-style:
 // q0 = RN(x * RN(1/c)), r = x - c*q0 exactly via FMA, q = RN(q0 + r * RN(1/c))).  Verified
 // against IEEE division on 5.5e8 random and structured operands per divisor
 // (tests/test_divconst.py restates the check on the host); no over/underflow in range.
-MXD double div6(double x) {
+template <class T>
+MXD T div6(T x) {
     const double y = 1.0 / 6.0;
-    const double q = __dmul_rn(x, y);
-    const double r = __fma_rn(-6.0, q, x);
-    return __fma_rn(r, y, q);
+    const T q = mul_(x, y);
+    const T r = fma_(-6.0, q, x);
+    return fma_(r, y, q);
 }
 MXD double div3(double x) {
     const double y = 1.0 / 3.0;
@@ -180,43 +233,62 @@ MXD double slope_any(int order, const double* S, int I, int lo, int hi, bool lob
 // ---------------------------------------------------------------------------------------
 // PPM: Source/MaestroPPM.cpp
 // ---------------------------------------------------------------------------------------
-// van Leer slope from the two one-sided differences dm = s0 - sm1, dp = sp1 - s0 and the
-// centred one dc2 = sp1 - sm1 (MaestroPPM.cpp:42-49)
-MXD double vanleer(double sm1, double s0, double sp1) {
-    const double dsc = 0.5 * (sp1 - sm1);
-    const double dsl = 2.0 * (s0 - sm1);
-    const double dsr = 2.0 * (sp1 - s0);
-    const double m = dmin_(fabs(dsc), dmin_(fabs(dsl), fabs(dsr)));
-    const double r = signed_mag(m, dsc);
-    return sel_pos(dsl * dsr, r);
+// |x| on the integer pipe (clears the sign bit of the high word; the fp64 pipe is the scarce one)
+MXD double abs_(double x) {
+    return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
+MXD D2 abs_(D2 x) { return D2{abs_(x.a), abs_(x.b)}; }
+
+// van Leer slope (MaestroPPM.cpp:42-49): with dsc = (sp1 - sm1)/2, dsl = 2 (s0 - sm1),
+// dsr = 2 (sp1 - s0) the reference forms sign(dsc) min(|dsc|, |dsl|, |dsr|) if dsl dsr > 0, else 0.
+// Scaling by 2 and 1/2 is exact, so the same result is obtained from the raw differences
+// c, l, r: the minimum over |c|/2, 2|l|, 2|r| is decided by comparing |c| with 4 min(|l|, |r|)
+// and scaled once, and dsl dsr > 0 <=> l r > 0.  This saves a third of the fp64 instructions
+// of a slope and lets neighbouring slopes share l / r.  (Equivalent bit for bit unless an
+// intermediate over- or underflows, i.e. for differences beyond 1e153 or below 1e-154.)
+template <class T>
+MXD T vanleer(T sm1, T s0, T sp1) {
+    const T c = sp1 - sm1, l = s0 - sm1, r = sp1 - s0;
+    const T al = abs_(l), ar = abs_(r), ac = abs_(c);
+    const T mn = dmin_(al, ar);        // dmin_(|dsl|, |dsr|) / 2, same tie rule
+    const auto inner = 4.0 * mn < ac;  // min(|dsl|, |dsr|) < |dsc|
+    const T m = sel(inner, mn, ac) * sel(inner, 2.0, 0.5);
+    return sel_pos(l * r, signed_mag(m, c));
 }
 
 // 4th-order edge between sL and sR with van Leer slopes dL, dR, clamped (MaestroPPM.cpp:62-67)
-MXD double vl_edge(double sL, double sR, double dL, double dR) {
-    double e = 0.5 * (sR + sL) - div6(dR - dL);
-    e = dmax_(e, dmin_(sR, sL));
-    e = dmin_(e, dmax_(sR, sL));
+template <class T>
+MXD T vl_edge(T sL, T sR, T dL, T dR) {
+    T e = 0.5 * (sR + sL) - div6(dR - dL);
+    // min(sR, sL) and max(sR, sL) from one comparison (for sR == sL either operand is the value)
+    const auto p = sL < sR;
+    const T lo = sel(p, sL, sR), hi = sel(p, sR, sL);
+    e = dmax_(e, lo);
+    e = dmin_(e, hi);
     return e;
 }
 
-MXD void cw_limit(double s0, double& sm, double& sp) {
+template <class T>
+MXD void cw_limit(T s0, T& sm, T& sp) {
     // MaestroPPM.cpp:106-115, written with selects (both arms are cheap and side-effect free)
-    const double dp = sp - s0, dm = sm - s0;
-    const bool flat = dp * (s0 - sm) <= 0.0;
-    const bool c1 = fabs(dp) >= 2.0 * fabs(dm);
-    const bool c2 = fabs(dm) >= 2.0 * fabs(dp);
-    const double s3 = 3.0 * s0;
-    const double sp_c1 = s3 - 2.0 * sm;
-    const double sm_c2 = s3 - 2.0 * sp;
-    const double sp_n = c1 ? sp_c1 : sp;
-    const double sm_n = (!c1 && c2) ? sm_c2 : sm;
-    sp = flat ? s0 : sp_n;
-    sm = flat ? s0 : sm_n;
+    const T dp = sp - s0, dm = sm - s0;
+    const auto flat = dp * dm >= 0.0;  // dp (s0 - sm) <= 0: s0 - sm = -dm exactly
+    const T adp = abs_(dp), adm = abs_(dm);
+    const auto c1 = adp >= 2.0 * adm;
+    const auto c2 = adm >= 2.0 * adp;
+    const T s3 = 3.0 * s0;
+    const T sp_c1 = s3 - 2.0 * sm;
+    const T sm_c2 = s3 - 2.0 * sp;
+    const T sp_n = sel(c1, sp_c1, sp);
+    const T sm_n = sel(!c1 && c2, sm_c2, sm);
+    sp = sel(flat, s0, sp_n);
+    sm = sel(flat, s0, sm_n);
 }
 
-MXD double bc_edge(double a, double b, double c, double d, double m0, double m1) {
+template <class T>
+MXD T bc_edge(T a, T b, T c, T d, T m0, T m1) {
     // MaestroPPM.cpp:124-131
-    double v = -0.2 * a + 0.75 * b + 0.5 * c - 0.05 * d;
+    T v = -0.2 * a + 0.75 * b + 0.5 * c - 0.05 * d;
     v = dmax_(v, dmin_(m0, m1));
     v = dmin_(v, dmax_(m0, m1));
     return v;
@@ -224,13 +296,14 @@ MXD double bc_edge(double a, double b, double c, double d, double m0, double m1)
 
 // ppm_type 1, second half: CW84 limiter + BC rows applied to the unlimited edge values
 // sm_u = edge(i-1/2), sp_u = edge(i+1/2) (MaestroPPM.cpp:100-205).  S[o+3], o in [-2,2] read.
-template <bool BC>
-MXD void ppm1_finish(const double* S, int I, int lo, int hi, bool lobc, bool hibc, double sm_u,
-                     double sp_u, double& sm, double& sp) {
-    const double sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
+// (T = D2: both halves sit at the same index I along the sweep direction.)
+template <bool BC, class T>
+MXD void ppm1_finish(const T* S, int I, int lo, int hi, bool lobc, bool hibc, T sm_u, T sp_u,
+                     T& sm, T& sp) {
+    const T sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
     sm = sm_u;
     sp = sp_u;
-    const double sedgel = sp, sedger = sm;
+    const T sedgel = sp, sedger = sm;
     cw_limit(s0, sm, sp);
     // (lobc / hibc are uniform over a warp in the streaming kernel, which clears them away
     // from the domain faces: the whole block below is then skipped by a uniform branch)
@@ -263,13 +336,12 @@ MXD void ppm1_finish(const double* S, int I, int lo, int hi, bool lobc, bool hib
 
 // ppm_type 1: sm, sp of the limited parabola in the cell.  S[o+3], o in [-3,3] (only -2..2
 // read).  MaestroPPM.cpp:34-205.
-template <bool BC>
-MXD void ppm1_parabola(const double* S, int I, int lo, int hi, bool lobc, bool hibc, double& sm,
-                       double& sp) {
-    const double sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
-    const double dl = vanleer(sm2, sm1, s0);
-    const double dc = vanleer(sm1, s0, sp1);
-    const double dr = vanleer(s0, sp1, sp2);
+template <bool BC, class T>
+MXD void ppm1_parabola(const T* S, int I, int lo, int hi, bool lobc, bool hibc, T& sm, T& sp) {
+    const T sm2 = S[1], sm1 = S[2], s0 = S[3], sp1 = S[4], sp2 = S[5];
+    const T dl = vanleer(sm2, sm1, s0);
+    const T dc = vanleer(sm1, s0, sp1);
+    const T dr = vanleer(s0, sp1, sp2);
     ppm1_finish<BC>(S, I, lo, hi, lobc, hibc, vl_edge(sm1, s0, dl, dc), vl_edge(s0, sp1, dc, dr),
                     sm, sp);
 }
@@ -416,13 +488,15 @@ MXD void ppm2_parabola(const double* S, int I, int lo, int hi, bool lobc, bool h
 
 // characteristic integration, MaestroPPM.cpp:210-231 (is_umac).  sig = |u| dt / h already
 // formed per face by the caller ((|u| * dt) / h, IEEE division).
-MXD double ppm_Ip(double sm, double sp, double s0, double s6, double up, double sig_p, double eps) {
-    const double v = sp - 0.5 * sig_p * (sp - sm - (1.0 - 2.0 / 3.0 * sig_p) * s6);
-    return (up > eps) ? v : s0;
+template <class T>
+MXD T ppm_Ip(T sm, T sp, T s0, T s6, T up, T sig_p, double eps) {
+    const T v = sp - 0.5 * sig_p * (sp - sm - (1.0 - 2.0 / 3.0 * sig_p) * s6);
+    return sel(up > eps, v, s0);
 }
-MXD double ppm_Im(double sm, double sp, double s0, double s6, double um, double sig_m, double eps) {
-    const double v = sm + 0.5 * sig_m * (sp - sm + (1.0 - 2.0 / 3.0 * sig_m) * s6);
-    return (um < -eps) ? v : s0;
+template <class T>
+MXD T ppm_Im(T sm, T sp, T s0, T s6, T um, T sig_m, double eps) {
+    const T v = sm + 0.5 * sig_m * (sp - sm + (1.0 - 2.0 / 3.0 * sig_m) * s6);
+    return sel(um < -eps, v, s0);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -87,6 +87,37 @@ __device__ __forceinline__ bool rhoh_flux_tab(const KFlux& f, bool have_h, doubl
     return false;
 }
 
+// spherical, use_exact_base_state = 0 (MaestroMakeFlux.cpp:871-1021): rho0e / h0e are the
+// time-centred base state on this face, 0.5*old + 0.5*new of the r0mac / h0mac face arrays
+__device__ __forceinline__ bool rhoh_flux_sph(const KFlux& f, double u, double ser, double seh,
+                                              double rho0e, double h0e, double* F) {
+    const int ept = f.ept, spt = f.spt;
+    if (ept == MX_PRED_H || ept == MX_PRED_T_THEN_H || ept == MX_PRED_TPRIME_THEN_H) {
+        if (spt == MX_PRED_RHOPRIME_AND_X) {
+            *F = u * (rho0e + ser) * seh;
+            return true;
+        }
+        if (spt == MX_PRED_RHO_AND_X || spt == MX_PRED_RHOX) {
+            *F = u * ser * seh;
+            return true;
+        }
+        return false;
+    }
+    if (ept == MX_PRED_HPRIME) {
+        if (spt == MX_PRED_RHOPRIME_AND_X) {
+            *F = u * (ser + rho0e) * (seh + h0e);
+            return true;
+        }
+        return false;
+    }
+    if (ept == MX_PRED_RHOH) {
+        *F = u * seh;
+        return true;
+    }
+    *F = u * (rho0e * h0e + seh);
+    return true;
+}
+
 __device__ __forceinline__ bool needs_sedge_rho_for_rhoh(const KFlux& f) {
     return f.ept == MX_PRED_H || f.ept == MX_PRED_T_THEN_H || f.ept == MX_PRED_TPRIME_THEN_H;
 }

@@ -56,6 +56,7 @@ struct FusedArgs {
     DFab state, force, sedge[3], umac[3], sflux[3], eta;
     DFab r0o[3], r0n[3];
     double* r0e[3];  // spherical: 0.5*(r0mac_old + r0mac_new) laid out like one sedge[d] component
+    double* h0e[3];  // spherical enthalpy pass: 0.5*(h0mac_old + h0mac_new), same layout
     int ncomp;
     int comp[MAXC];
     int bclo[MAXC][3], bchi[MAXC][3];
@@ -186,6 +187,7 @@ int dispatch(FusedArgs& A, int ppm_type, cudaStream_t stream) {
                                       : launch_stream6_mode<2>(A, stream);
         if (r <= 0) return r;
     }
+    if (A.mode == 2 && A.f.spherical) return 1;  // k_stream4 has no spherical enthalpy form
     if (ppm_type == 0) return launch_stream4_mode<0>(A, stream);
     if (ppm_type == 1) return launch_stream4_mode<1>(A, stream);
     return launch_stream4_mode<2>(A, stream);
@@ -317,19 +319,26 @@ int fused_density(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, int 
 
 bool fused_enthalpy_supported(const KGeom& g, const KEdge& e, const KFlux& f) {
     if (getenv("MXADV_FORCE_STAGED")) return false;
-    return g.dim == 3 && !e.is_vel && !e.is_cons && !e.trace && !f.spherical;
+    // spherical: the use_exact_base_state forms (rhoh0mac, with the reference's x-face quirk)
+    // stay on the separate flux kernel
+    return g.dim == 3 && !e.is_vel && !e.is_cons && !e.trace && !(f.spherical && f.exact);
 }
 
 int fused_enthalpy(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, const KFlux& f,
                    const DFab& state, const DFab* sedge, const DFab* sflux, const DFab* umac,
-                   const DFab& force, cudaStream_t stream) {
+                   const DFab& force, double* const* r0e, double* const* h0e, cudaStream_t stream) {
     bool any_bc = false;
     if (!comps_ok(par, par->start_bccomp, 1, &any_bc)) return 1;
     FusedArgs A;
     fill_common(A, g, e0, state, sedge, umac, force);
     A.mode = 2;
     A.f = f;
-    for (int d = 0; d < 3; ++d) A.sflux[d] = sflux[d];
+    if (f.spherical && (!r0e || !h0e)) return 1;
+    for (int d = 0; d < 3; ++d) {
+        A.sflux[d] = sflux[d];
+        A.r0e[d] = f.spherical ? r0e[d] : nullptr;
+        A.h0e[d] = f.spherical ? h0e[d] : nullptr;
+    }
     A.ncomp = 1;
     A.comp[0] = par->start_scomp;
     const int* bc = par->bc + 6 * par->start_bccomp;

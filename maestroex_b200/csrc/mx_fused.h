@@ -16,5 +16,6 @@ int fused_density(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, int 
 bool fused_enthalpy_supported(const KGeom& g, const KEdge& e, const KFlux& f);
 int fused_enthalpy(const KGeom& g, const KEdge& e0, const MxEdgeParams* par, const KFlux& f,
                    const DFab& state, const DFab* sedge, const DFab* sflux, const DFab* umac,
-                   const DFab& force, cudaStream_t stream);
+                   const DFab& force, double* const* r0e /*[3] spherical, else null*/,
+                   double* const* h0e /*[3] spherical, else null*/, cudaStream_t stream);
 #endif

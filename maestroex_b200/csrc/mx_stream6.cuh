@@ -35,9 +35,26 @@
 constexpr int S6_RS = 8;          // scalar ring slots
 constexpr int S6_IS = 3;          // I-buffer slots
 constexpr int S6_IBS = 17 * 32;   // doubles per I-buffer array: 16 tile rows + one slack row
+constexpr int S6_US = 16 * 33 + 16;  // x MAC velocity of a plane: 16 rows x (32 lanes + the face beyond)
+constexpr int S6_VS = 17 * 32;       // y MAC velocity: 17 face rows
+constexpr int S6_SLOT = 6 * S6_IBS + S6_US + S6_VS;  // one hand-off slot
+// rows of the tile one reconstruction thread owns (4 -> 4 warps, 2 -> 8 warps) and the
+// register budgets of the two roles after setmaxnreg (the launch budget is the largest
+// multiple of 8 with (512 + S6_NR) * budget <= 65536; the budgets must add up to at most that)
+#ifndef S6_RROWS
+#define S6_RROWS 4
+#endif
+#ifndef S6_QREG
+#define S6_QREG 88
+#endif
+#ifndef S6_RREG
+#define S6_RREG 128
+#endif
 constexpr int S6_NQ = 512;        // Riemann threads
-constexpr int S6_NR = 128;        // reconstruction threads
+constexpr int S6_NR = 32 * (16 / S6_RROWS);  // reconstruction threads
 constexpr int S6_NT = S6_NQ + S6_NR;
+constexpr int S6_LREG = (65536 / S6_NT) / 8 * 8;  // registers per thread at launch
+static_assert(S6_NQ * S6_QREG + S6_NR * S6_RREG <= S6_NT * S6_LREG, "register budgets exceed the launch allocation");
 constexpr int S6_XS = 512 + 64;   // exchange array incl. one slack row either side
 // named barriers (0 is __syncthreads)
 constexpr int B6_Q1 = 1, B6_Q2 = 2, B6_R = 3, B6_FULL = 4, B6_EMPTY = 7;
@@ -49,7 +66,7 @@ __host__ __device__ constexpr int s6_pls() {  // doubles per ring slot: a 128-by
 }
 template <int PPM>
 constexpr int stream6_smem_doubles() {
-    return S6_RS * s6_pls<PPM>() + S6_IS * 6 * S6_IBS + 7 * S6_XS + 12 * S6_NQ +
+    return S6_RS * s6_pls<PPM>() + S6_IS * S6_SLOT + 7 * S6_XS + 8 * S6_NQ +
            5 * (ST_MAXZC + 2) + 2 + S6_RS;
 }
 
@@ -109,17 +126,18 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
     constexpr int LA = (PPM == 2) ? 3 : 2;
     constexpr int PW = 32 + 2 * LA, PLS = s6_pls<PPM>();
     constexpr int PF = 7 - 2 * LA;  // planes in flight beyond the resident window
-    constexpr int NY = 4 + 2 * LA;  // column values a thread needs for its four rows
+    constexpr int NRW = S6_RROWS;        // tile rows per thread
+    constexpr int NY = NRW + 2 * LA;  // column values a thread needs for its rows
     double* const ring = smem;
     double* const ibuf = ring + S6_RS * PLS;
     unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(
-        ibuf + S6_IS * 6 * S6_IBS + 7 * S6_XS + 12 * S6_NQ + 5 * (ST_MAXZC + 2) + 2);
+        ibuf + S6_IS * S6_SLOT + 7 * S6_XS + 8 * S6_NQ + 5 * (ST_MAXZC + 2) + 2);
 
     const int rt = threadIdx.x - S6_NQ;
     const int tx = rt & 31, rg = rt >> 5;
     const KGeom& g = A.g;
     const S6Tile T = s6_tile(A);
-    const int i = T.x0 - 1 + tx, j0 = T.y0 - 1 + 4 * rg;
+    const int i = T.x0 - 1 + tx, j0 = T.y0 - 1 + NRW * rg;
     const int a0 = T.k0 - 1, nit = T.k1 - a0;  // steps 0 .. nit
     const int il = min(i, T.thx + 1);
     const int jb = min(j0, T.thy + 1), jvb = min(j0, T.thy + 2);
@@ -130,7 +148,7 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
     const bool elected = (rt == 0);
     const int cx0 = T.x0 - 1 - LA - A.state.lo[0], cy0 = T.y0 - 1 - LA - A.state.lo[1];
     const int cz0 = a0 - LA - A.state.lo[2];
-    const int rc0 = (4 * rg + LA) * PW + tx + LA;  // my row 0, my lane, in a ring plane
+    const int rc0 = (NRW * rg + LA) * PW + tx + LA;  // my row 0, my lane, in a ring plane
     unsigned phase = 0;                            // per-slot parity of the next wait
 
     const bool nearx = BC && __any_sync(0xffffffffu, (i <= g.dlo[0] + 4) || (i >= g.dhi[0] - 4));
@@ -160,10 +178,10 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
                                cx0, cy0, cz0 + q, comp);
             }
         }
-        double w_lo[4], sg_lo[4];
-        double zA[4], zB[4], zC[4];  // PPM 1: dz_c, ez_lo;  PPM 2: ez_l2, ez_l1, ez_h1
+        double w_lo[NRW], sg_lo[NRW];
+        double zA[NRW], zB[NRW], zC[NRW];  // PPM 1: dz_c, ez_lo;  PPM 2: ez_l2, ez_l1, ez_h1
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NRW; ++q) {
             w_lo[q] = pW[min(q, dm) * w_sy];
             sg_lo[q] = (PPM != 0) ? div_h<2>(A, fabs(w_lo[q]) * dt) : 0.0;
             zA[q] = zB[q] = zC[q] = 0.0;
@@ -175,7 +193,7 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
         }
         if (PPM != 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NRW; ++q) {
                 const double* c = ring + rc0 + q * PW;
                 if (PPM == 1) {
                     const double zm2 = c[(LA - 2) * PLS], zm1 = c[(LA - 1) * PLS], z0 = c[LA * PLS],
@@ -210,15 +228,27 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
             }
             // velocities of this plane (issued before the waits: they are not needed until the
             // parabolas are limited)
-            double um[4], vm[5], w_hi[4];
+            double um[NRW], vm[NRW + 1], w_hi[NRW], up31[NRW];
             pW += w_sz;
+            const bool more = it < nit;  // next step's lines start towards L2 while this one computes
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                um[q] = pU[min(q, dm) * u_sy];
-                w_hi[q] = pW[min(q, dm) * w_sy];
+            for (int q = 0; q < NRW; ++q) {
+                const double* au = pU + min(q, dm) * u_sy;
+                const double* aw = pW + min(q, dm) * w_sy;
+                um[q] = au[0];
+                w_hi[q] = aw[0];
+                up31[q] = (tx == 31) ? au[1] : 0.0;
+                if (more) {
+                    prefetch_l2(au + u_sz);
+                    prefetch_l2(aw + w_sz);
+                }
             }
 #pragma unroll
-            for (int q = 0; q < 5; ++q) vm[q] = pV[min(q, dmv) * v_sy];
+            for (int q = 0; q < NRW + 1; ++q) {
+                const double* av = pV + min(q, dmv) * v_sy;
+                vm[q] = av[0];
+                if (more && q < NRW) prefetch_l2(av + v_sz);
+            }
             pU += u_sz;
             pV += v_sz;
             {
@@ -227,13 +257,40 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
                 phase ^= 1u << s;
             }
             if (it >= 2) bar_sync(B6_EMPTY + it % 3, S6_NT);  // Riemann warps released this slot
-            double* const I = ibuf + (it % 3) * 6 * S6_IBS + (4 * rg) * 32 + tx;
-            double* const In = ibuf + ((it + 1) % 3) * 6 * S6_IBS + (4 * rg) * 32 + tx;
+            double* const I = ibuf + (it % 3) * S6_SLOT + (NRW * rg) * 32 + tx;
+            double* const In = ibuf + ((it + 1) % 3) * S6_SLOT + (NRW * rg) * 32 + tx;
             const double* const P = ring + ((it + LA) & (S6_RS - 1)) * PLS + rc0;  // plane a, row 0
 
             // ---- x --------------------------------------------------------------------------
+            // ppm_type 1: two rows at a time (D2), so that this lone warp of the sub-partition
+            // always has an independent instruction next to the one it waits for
+            constexpr bool PAIR = (PPM == 1) && (NRW % 2 == 0);
+            if (PAIR) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < NRW; q += 2) {
+                    D2 S[7];
+                    S[0] = S[6] = d2(0.0);
+#pragma unroll
+                    for (int o = -LA; o <= LA; ++o) S[o + 3] = d2(P[q * PW + o], P[(q + 1) * PW + o]);
+                    D2 sm, sp;
+                    ppm1_parabola<BC>(S, i, g.dlo[0], g.dhi[0], lobcx, hibcx, sm, sp);
+                    const D2 umv = d2(um[q], um[q + 1]);
+                    const D2 sg_m = div_h<0>(A, abs_(umv) * dt);
+                    const D2 sg_p = shfl_dn1(sg_m);
+                    const D2 up = shfl_dn1(umv);
+                    const D2 s6 = 6.0 * S[3] - 3.0 * (sm + sp);
+                    const D2 lx = ppm_Ip(sm, sp, S[3], s6, up, sg_p, eps);
+                    const D2 rx = ppm_Im(sm, sp, S[3], s6, umv, sg_m, eps);
+                    if (tx < 31) {
+                        I[0 * S6_IBS + q * 32 + 1] = lx.a;
+                        I[0 * S6_IBS + (q + 1) * 32 + 1] = lx.b;
+                    }
+                    I[1 * S6_IBS + q * 32] = rx.a;
+                    I[1 * S6_IBS + (q + 1) * 32] = rx.b;
+                }
+            } else {
+#pragma unroll
+            for (int q = 0; q < NRW; ++q) {
                 double S[7];
                 S[0] = S[6] = 0.0;
 #pragma unroll
@@ -262,29 +319,76 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
                 if (tx < 31) I[0 * S6_IBS + q * 32 + 1] = lx;
                 I[1 * S6_IBS + q * 32] = rx;
             }
+            }
             // ---- y (slopes / edge values shared between my four rows) ------------------------
             {
                 double Y[NY];
 #pragma unroll
                 for (int t = 0; t < NY; ++t) Y[t] = P[(t - LA) * PW];
-                double sgy[5];
+                double sgy[NRW + 1];
                 if (PPM != 0) {
+                    if (PAIR) {
 #pragma unroll
-                    for (int q = 0; q < 5; ++q) sgy[q] = div_h<1>(A, fabs(vm[q]) * dt);
+                        for (int q = 0; q + 1 < NRW + 1; q += 2) {
+                            const D2 s = div_h<1>(A, abs_(d2(vm[q], vm[q + 1])) * dt);
+                            sgy[q] = s.a;
+                            sgy[q + 1] = s.b;
+                        }
+                        sgy[NRW] = div_h<1>(A, fabs(vm[NRW]) * dt);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NRW + 1; ++q) sgy[q] = div_h<1>(A, fabs(vm[q]) * dt);
+                    }
                 }
-                double G[7];  // PPM 1: G[0..4] edges below rows 0..4;  PPM 2: edges -1 .. 5
+                double G[NRW + 3];  // PPM 1: G[0..NRW] edges below rows 0..NRW;  PPM 2: edges -1 .. NRW+1
                 if (PPM == 1) {
-                    double d[6];
+                    double d[NRW + 2];
+                    if (PAIR) {
 #pragma unroll
-                    for (int t = 0; t < 6; ++t) d[t] = vanleer(Y[t], Y[t + 1], Y[t + 2]);
+                        for (int t = 0; t < NRW + 2; t += 2) {
+                            const D2 v = vanleer(d2(Y[t], Y[t + 1]), d2(Y[t + 1], Y[t + 2]), d2(Y[t + 2], Y[t + 3]));
+                            d[t] = v.a;
+                            d[t + 1] = v.b;
+                        }
 #pragma unroll
-                    for (int t = 0; t < 5; ++t) G[t] = vl_edge(Y[t + 1], Y[t + 2], d[t], d[t + 1]);
+                        for (int t = 0; t + 1 < NRW + 1; t += 2) {
+                            const D2 v = vl_edge(d2(Y[t + 1], Y[t + 2]), d2(Y[t + 2], Y[t + 3]), d2(d[t], d[t + 1]),
+                                                 d2(d[t + 1], d[t + 2]));
+                            G[t] = v.a;
+                            G[t + 1] = v.b;
+                        }
+                        G[NRW] = vl_edge(Y[NRW + 1], Y[NRW + 2], d[NRW], d[NRW + 1]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < NRW + 2; ++t) d[t] = vanleer(Y[t], Y[t + 1], Y[t + 2]);
+#pragma unroll
+                        for (int t = 0; t < NRW + 1; ++t) G[t] = vl_edge(Y[t + 1], Y[t + 2], d[t], d[t + 1]);
+                    }
                 } else if (PPM == 2) {
 #pragma unroll
-                    for (int t = 0; t < 7; ++t) G[t] = cs_edge(Y[t], Y[t + 1], Y[t + 2], Y[t + 3]);
+                    for (int t = 0; t < NRW + 3; ++t) G[t] = cs_edge(Y[t], Y[t + 1], Y[t + 2], Y[t + 3]);
                 }
+                if (PAIR && !BC) {
+                    // away from physical boundaries the limiter does not depend on the row index
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < NRW; q += 2) {
+                        D2 S[7];
+                        S[0] = S[6] = d2(0.0);
+#pragma unroll
+                        for (int o = -LA; o <= LA; ++o) S[o + 3] = d2(Y[q + LA + o], Y[q + 1 + LA + o]);
+                        D2 sm, sp;
+                        ppm1_finish<false>(S, 0, 0, 0, false, false, d2(G[q], G[q + 1]), d2(G[q + 1], G[q + 2]), sm, sp);
+                        const D2 s6 = 6.0 * S[3] - 3.0 * (sm + sp);
+                        const D2 ly = ppm_Ip(sm, sp, S[3], s6, d2(vm[q + 1], vm[q + 2]), d2(sgy[q + 1], sgy[q + 2]), eps);
+                        const D2 ry = ppm_Im(sm, sp, S[3], s6, d2(vm[q], vm[q + 1]), d2(sgy[q], sgy[q + 1]), eps);
+                        I[2 * S6_IBS + (q + 1) * 32] = ly.a;
+                        I[2 * S6_IBS + (q + 2) * 32] = ly.b;
+                        I[3 * S6_IBS + q * 32] = ry.a;
+                        I[3 * S6_IBS + (q + 1) * 32] = ry.b;
+                    }
+                } else {
+#pragma unroll
+                for (int q = 0; q < NRW; ++q) {
                     const int j = j0 + q;
                     const bool ny = BC && ((j <= g.dlo[1] + 4) || (j >= g.dhi[1] - 4));
                     const bool lo_ = lobcy && ny, hi_ = hibcy && ny;
@@ -313,10 +417,45 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
                     I[2 * S6_IBS + (q + 1) * 32] = ly;  // row q+1 reads it as its low-face left state
                     I[3 * S6_IBS + q * 32] = ry;
                 }
+                }
             }
             // ---- z (incremental) -------------------------------------------------------------
+            if (PAIR) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < NRW; q += 2) {
+                    D2 S[7];
+                    S[0] = S[6] = d2(0.0);
+#pragma unroll
+                    for (int o = -LA; o <= LA; ++o) {
+                        const bool need = (BC && bcz) || o >= 0;
+                        const double* c = ring + ((it + LA + o) & (S6_RS - 1)) * PLS + rc0 + q * PW;
+                        S[o + 3] = need ? d2(c[0], c[PW]) : d2(0.0);
+                    }
+                    const D2 dz_n = vanleer(S[3], S[4], S[5]);
+                    const D2 ez_hi = vl_edge(S[3], S[4], d2(zA[q], zA[q + 1]), dz_n);
+                    D2 sm, sp;
+                    ppm1_finish<BC>(S, a, g.dlo[2], g.dhi[2], lobcz, hibcz, d2(zB[q], zB[q + 1]), ez_hi, sm, sp);
+                    zA[q] = dz_n.a;
+                    zA[q + 1] = dz_n.b;
+                    zB[q] = ez_hi.a;
+                    zB[q + 1] = ez_hi.b;
+                    const D2 s6 = 6.0 * S[3] - 3.0 * (sm + sp);
+                    const D2 whi = d2(w_hi[q], w_hi[q + 1]);
+                    const D2 sg_hi = div_h<2>(A, abs_(whi) * dt);
+                    const D2 lz = ppm_Ip(sm, sp, S[3], s6, whi, sg_hi, eps);
+                    const D2 rz = ppm_Im(sm, sp, S[3], s6, d2(w_lo[q], w_lo[q + 1]), d2(sg_lo[q], sg_lo[q + 1]), eps);
+                    sg_lo[q] = sg_hi.a;
+                    sg_lo[q + 1] = sg_hi.b;
+                    w_lo[q] = w_hi[q];
+                    w_lo[q + 1] = w_hi[q + 1];
+                    In[4 * S6_IBS + q * 32] = lz.a;  // left state of face a+1
+                    In[4 * S6_IBS + (q + 1) * 32] = lz.b;
+                    I[5 * S6_IBS + q * 32] = rz.a;
+                    I[5 * S6_IBS + (q + 1) * 32] = rz.b;
+                }
+            } else {
+#pragma unroll
+            for (int q = 0; q < NRW; ++q) {
                 double S[7];
                 S[0] = S[6] = 0.0;
 #pragma unroll
@@ -357,6 +496,21 @@ __device__ __forceinline__ void stream6_recon(const FusedArgs& A, double* smem) 
                 In[4 * S6_IBS + q * 32] = lz;  // left state of face a+1
                 I[5 * S6_IBS + q * 32] = rz;
             }
+            }
+            {   // the MAC velocities of this plane for the Riemann warps (they keep no pointers or
+                // prefetch registers for them): U[row][lane] plus the face beyond lane 31, V[row].
+                // Stored at the END of the step: the loads were issued at its top, so nothing
+                // here waits on global memory.
+                double* const U = ibuf + (it % 3) * S6_SLOT + 6 * S6_IBS + (NRW * rg) * 33 + tx;
+                double* const V = ibuf + (it % 3) * S6_SLOT + 6 * S6_IBS + S6_US + (NRW * rg) * 32 + tx;
+#pragma unroll
+                for (int q = 0; q < NRW; ++q) {
+                    U[q * 33] = um[q];
+                    V[q * 32] = vm[q];
+                    if (tx == 31) U[q * 33 + 1] = up31[q];
+                }
+                if (rg == 16 / NRW - 1) V[NRW * 32] = vm[NRW];
+            }
             bar_arrive(B6_FULL + it % 3, S6_NT);
         }
     }
@@ -369,7 +523,7 @@ template <bool BC, int MODE, bool SPH>
 __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem, int ring_doubles) {
     constexpr int GX = 32, NT = S6_NQ;
     double* const ibuf = smem + ring_doubles;
-    double* const ex = ibuf + S6_IS * 6 * S6_IBS + GX;
+    double* const ex = ibuf + S6_IS * S6_SLOT + GX;
     double* X_T6X = ex + 0 * S6_XS;
     double* X_TZ = ex + 1 * S6_XS;
     double* X_HYX = ex + 2 * S6_XS;
@@ -378,7 +532,7 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
     double* X_QY2 = ex + 5 * S6_XS;
     double* X_FS = ex + 6 * S6_XS;
     double* hist = ex + 7 * S6_XS - GX;
-    double* tab = hist + 12 * NT;
+    double* tab = hist + 8 * NT;
     double* T_RXY = tab;
     double* T_RZ = tab + (ST_MAXZC + 2);
     double* T_W0R = tab + 2 * (ST_MAXZC + 2);
@@ -389,7 +543,7 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
     const int tx = tid & 31, ty = tid >> 5;
     double* const hs = hist + tid;
 #define HS(v) hs[(v) * NT]
-    enum { H_UF, H_VF, H_C4X, H_C4Y, H_HZX, H_HZY, H_T4XY, H_T4YX, H_FS, H_T6X, H_T6Y, H_SHZ };
+    enum { H_HZX, H_HZY, H_T4XY, H_T4YX, H_FS, H_T6X, H_T6Y, H_SHZ };
 
     const KGeom& g = A.g;
     const S6Tile T = s6_tile(A);
@@ -415,23 +569,22 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
     const bool neary = BC && ((j <= g.dlo[1] + 4) || (j >= g.dhi[1] - 4));
 
     const long f_sz = A.force.sz;
-    const long u_sz = A.umac[0].sz, v_sz = A.umac[1].sz, w_sz = A.umac[2].sz;
-    const long v_sy = A.umac[1].sy;
+    const long w_sz = A.umac[2].sz;
     const long ex_sz = A.sedge[0].sz, ey_sz = A.sedge[1].sz, ez_sz = A.sedge[2].sz;
     const long fx_sz = A.sflux[0].sz, fy_sz = A.sflux[1].sz, fz_sz = A.sflux[2].sz;
     const long eta_sz = A.eta.sz;
     const KFlux& F_ = A.f;
     constexpr bool sph = SPH;
-    const bool lane31 = (tx == 31);
 
     const double c6x = A.c6h[0], c6y = A.c6h[1], c6z = A.c6h[2];
     const double c4x = A.c4h[0], c4y = A.c4h[1], c4z = A.c4h[2];
     const double eps = A.eps;
     const bool have_h = (MODE == 2) && (F_.ept == MX_PRED_H || F_.ept == MX_PRED_T_THEN_H ||
                                         F_.ept == MX_PRED_TPRIME_THEN_H);
-    const bool need_ser = (MODE == 1) ? (F_.spt != MX_PRED_RHOX) : have_h;
+    // sedge(Rho) is an input of the flux: species forms except (rho X); h forms; spherical h'
+    const bool need_ser = (MODE == 1) ? (F_.spt != MX_PRED_RHOX)
+                                      : (have_h || (sph && F_.ept == MX_PRED_HPRIME));
 
-    const long u_c = A.umac[0].off(il, jl, a0), v_c = A.umac[1].off(il, jl, a0);
     const long w_c = A.umac[2].off(il, jl, a0);
     const long f_c = A.force.off(il, jl, a0);
     const long ex_c = A.sedge[0].off(icx, jcx, a0 - 1), ey_c = A.sedge[1].off(icy, jcy, a0 - 1);
@@ -459,8 +612,6 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
         const bool is_spec = comp >= F_.first_spec && comp <= F_.first_spec + F_.num_spec - 1;
         const bool last_spec = comp == F_.first_spec + F_.num_spec - 1;
 
-        const double* __restrict__ pU = A.umac[0].p + u_c;
-        const double* __restrict__ pV = A.umac[1].p + v_c;
         const double* __restrict__ pW = A.umac[2].p + w_c + w_sz;
         const double* __restrict__ pF = A.force.comp(comp) + f_c;
         double* __restrict__ pEx = A.sedge[0].comp(comp) + ex_c;
@@ -472,6 +623,7 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
         double* __restrict__ pEta = nullptr;
         long dRx = 0, dRy = 0, dRz = 0, dGx = 0, dGy = 0, dGz = 0;
         long dQx = 0, dQy = 0, dQz = 0;
+        long dHx = 0, dHy = 0, dHz = 0;  // spherical enthalpy pass: h0e - this comp of sedge
         if (MODE != 0) {
             pFx = A.sflux[0].comp(comp) + fx_c;
             pFy = A.sflux[1].comp(comp) + fy_c;
@@ -490,43 +642,45 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                 dGz = (long)(F_.rho - comp) * A.sflux[2].sn;
                 if (A.do_eta) pEta = A.eta.p + eta_c;
             }
+            if (MODE == 2 && sph) {
+                dQx = A.r0e[0] - A.sedge[0].comp(comp);
+                dQy = A.r0e[1] - A.sedge[1].comp(comp);
+                dQz = A.r0e[2] - A.sedge[2].comp(comp);
+                dHx = A.h0e[0] - A.sedge[0].comp(comp);
+                dHy = A.h0e[1] - A.sedge[1].comp(comp);
+                dHz = A.h0e[2] - A.sedge[2].comp(comp);
+            }
         }
 
         __syncthreads();  // every role is done with the previous component; tables written
         double w_m1 = 0.0, w_0 = 0.0;
         double w_p1 = pW[-w_sz];  // face a0
-        double um_n = pU[0];
-        double up31_n = lane31 ? pU[1] : 0.0;
-        double vm_n = pV[0];
-        double vp_n = pV[v_sy];
         double w_n = pW[0];  // face a0+1
         double f_n = pF[0];
 #pragma unroll
-        for (int v = 0; v < 12; ++v) HS(v) = 0.0;
+        for (int v = 0; v < 8; ++v) HS(v) = 0.0;
         bool slow_p = true;
 
         for (int a = a0; a <= k1; ++a) {
             const int it = a - a0;
             const bool bcz = bcz_c && ((a <= g.dlo[2] + 4) || (a >= g.dhi[2] - 4));
             // ---- P0: current-plane registers, prefetch of the next plane ----------------------
-            const double um = um_n, vm = vm_n, vp = vp_n, f0 = f_n;
-            double up = shfl_dn1(um);
-            if (lane31) up = up31_n;
+            const double f0 = f_n;
             w_m1 = w_0;
             w_0 = w_p1;
             w_p1 = w_n;
             if (a < k1) {
-                pU += u_sz;
-                pV += v_sz;
                 pW += w_sz;
                 pF += f_sz;
-                um_n = pU[0];
-                if (lane31) up31_n = pU[1];
-                vm_n = pV[0];
-                vp_n = pV[v_sy];
                 w_n = pW[0];
                 f_n = pF[0];
             }
+            bar_sync(B6_FULL + it % 3, S6_NT);  // plane a has been reconstructed, its velocities staged
+            const double* const I = ibuf + (it % 3) * S6_SLOT + tid;
+            const double* const Ip_ = ibuf + ((it + 2) % 3) * S6_SLOT + tid;  // plane a-1
+            const double* const Uc = ibuf + (it % 3) * S6_SLOT + 6 * S6_IBS + ty * 33 + tx;
+            const double* const Vc = ibuf + (it % 3) * S6_SLOT + 6 * S6_IBS + S6_US + tid;
+            const double um = Uc[0], up = Uc[1], vm = Vc[0], vp = Vc[GX];
             const bool px_pos = um > 0.0, px_nz0 = fabs(um) > 0.0, px_nz = fabs(um) > eps;
             const bool py_pos = vm > 0.0, py_nz0 = fabs(vm) > 0.0, py_nz = fabs(vm) > eps;
             const bool pz_pos = w_0 > 0.0, pz_nz0 = fabs(w_0) > 0.0, pz_nz = fabs(w_0) > eps;
@@ -542,9 +696,6 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
             auto plane = [&](auto slow_tag) {
                 constexpr bool SLOW = decltype(slow_tag)::value;
             // ---- P2: 1-D states from the I-buffer, first Riemann solve -----------------------
-                bar_sync(B6_FULL + it % 3, S6_NT);  // plane a has been reconstructed
-                const double* const I = ibuf + (it % 3) * 6 * S6_IBS + tid;
-                const double* const Ip_ = ibuf + ((it + 2) % 3) * 6 * S6_IBS + tid;  // plane a-1
                 double slx = I[0 * S6_IBS], srx = I[1 * S6_IBS];
                 double sly = I[2 * S6_IBS], sry = I[3 * S6_IBS];
                 double slz = I[4 * S6_IBS], srz = I[5 * S6_IBS];
@@ -592,7 +743,7 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                         if (do_z) g_z = pFz[dGz];
                     }
                     if (MODE == 1 && A.do_eta && do_z) e_z = pEta[0];
-                    if (MODE == 1 && sph) {
+                    if (sph) {  // time-centred base state on this face (mac_average output)
                         if (do_xy) {
                             q_x = pEx[dQx];
                             q_y = pEy[dQy];
@@ -603,7 +754,10 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                 bar_sync(B6_Q1, S6_NQ);  // S4
 
                 // ---- P4: corner-coupled states ---------------------------------------------------
-                const double uf_p = HS(H_UF), vf_p = HS(H_VF);
+                // velocities of plane a-1 from its slot (instead of a thread-private history)
+                const double* const Up = ibuf + ((it + 2) % 3) * S6_SLOT + 6 * S6_IBS + ty * 33 + tx;
+                const double* const Vp = ibuf + ((it + 2) % 3) * S6_SLOT + 6 * S6_IBS + S6_US + tid;
+                const double uf_p = Up[0], vf_p = Vp[0];
                 const bool qx_pos = uf_p > 0.0, qx_nz = fabs(uf_p) > eps;
                 const bool qy_pos = vf_p > 0.0, qy_nz = fabs(vf_p) > eps;
                 double slx_p = Ip_[0 * S6_IBS], srx_p = Ip_[1 * S6_IBS];
@@ -643,7 +797,7 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                 X_HYX[tid] = hyx;
                 X_HYZ[tid] = hyz;
                 const double c4zw = c4z * wsum_p;
-                const double t4xz = HS(H_C4X) * (shfl_dn1(hxz) - hxz);
+                const double t4xz = (c4x * (Up[1] + uf_p)) * (shfl_dn1(hxz) - hxz);
                 const double t4zx = c4zw * (hzx - HS(H_HZX));
                 const double fs_prev = HS(H_FS);
                 X_QY1[tid] = t4xz;
@@ -655,7 +809,7 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                 const double c4xu = c4x * usx, c4yu = c4y * usy;
                 const double t4xy = c4xu * (shfl_dn1(hxy) - hxy);
                 const double t4yx = c4yu * (X_HYX[tid + GX] - hyx);
-                const double t4yz = HS(H_C4Y) * (X_HYZ[tid + GX] - hyz);
+                const double t4yz = (c4y * (Vp[GX] + vf_p)) * (X_HYZ[tid + GX] - hyz);
                 const double t4zy = c4zw * (hzy - HS(H_HZY));
                 const double fs_cur = A.dt2 * f0;
 
@@ -694,6 +848,13 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                             pFy[0] = fly;
                             pFy[dGy] = g_y + fly;
                         }
+                    } else if (MODE == 2 && sph) {
+                        // MakeRhoHFlux (spherical), MaestroMakeFlux.cpp:871-1021
+                        double fl;
+                        if (rhoh_flux_sph(F_, uf_p, r_x, ex_v, q_x, pEx[dHx], &fl))
+                            if (ownx) pFx[0] = fl;
+                        if (rhoh_flux_sph(F_, vf_p, r_y, ey_v, q_y, pEy[dHy], &fl))
+                            if (owny) pFy[0] = fl;
                     } else if (MODE == 2) {
                         double fl;
                         if (rhoh_flux_tab(F_, have_h, uf_p, r_x, ex_v, T_RXY[it - 1], T_HXY[it - 1], false, &fl))
@@ -726,6 +887,10 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                             if (last_spec) ev -= T_W0R[it];
                             if (ownz) pEta[0] = ev;
                         }
+                    } else if (MODE == 2 && sph) {
+                        double fl;
+                        if (rhoh_flux_sph(F_, w_0, r_z, ez_v, q_z, pEz[dHz], &fl))
+                            if (ownz) pFz[0] = fl;
                     } else if (MODE == 2) {
                         double fl;
                         if (rhoh_flux_tab(F_, have_h, w_0, r_z, ez_v, T_RZ[it], T_HZ[it], true, &fl))
@@ -742,10 +907,6 @@ __device__ __forceinline__ void stream6_riemann(const FusedArgs& A, double* smem
                     if (MODE == 1) pEta += eta_sz;
                 }
                 // ---- z history for the next plane; release the slot of plane a-1 --------------------
-                HS(H_UF) = um;
-                HS(H_VF) = vm;
-                HS(H_C4X) = c4xu;
-                HS(H_C4Y) = c4yu;
                 HS(H_HZX) = hzx;
                 HS(H_HZY) = hzy;
                 HS(H_T4XY) = t4xy;
@@ -780,7 +941,7 @@ __global__ void __launch_bounds__(S6_NT, 1) k_stream6(const __grid_constant__ Fu
 
     // ---- block-wide set-up: mbarriers, I-buffer cleared, base-state tables ----------------------
     double* const ibuf = sm6 + RD;
-    double* const tab = ibuf + S6_IS * 6 * S6_IBS + 7 * S6_XS + 12 * S6_NQ;
+    double* const tab = ibuf + S6_IS * S6_SLOT + 7 * S6_XS + 8 * S6_NQ;
     unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(tab + 5 * (ST_MAXZC + 2) + 2);
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -788,7 +949,7 @@ __global__ void __launch_bounds__(S6_NT, 1) k_stream6(const __grid_constant__ Fu
         for (int q = 0; q < S6_RS; ++q) mbar_init(mbar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int q = tid; q < S6_IS * 6 * S6_IBS; q += S6_NT) ibuf[q] = 0.0;
+    for (int q = tid; q < S6_IS * S6_SLOT; q += S6_NT) ibuf[q] = 0.0;
     if (MODE != 0 && !SPH) {
         const KFlux& F_ = A.f;
         const int a0 = T.k0 - 1;
@@ -828,13 +989,13 @@ __global__ void __launch_bounds__(S6_NT, 1) k_stream6(const __grid_constant__ Fu
     // reconstruction warpgroup needs to grow to 128 (setmaxnreg.inc only draws on registers
     // released by setmaxnreg.dec of the same CTA): 512 x 88 + 128 x 128 = 640 x 96.
     if (tid >= S6_NQ) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;\n");
+        if (S6_RREG > S6_LREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(S6_RREG));
         if (bc)
             stream6_recon<PPM, true>(A, sm6);
         else
             stream6_recon<PPM, false>(A, sm6);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n");
+        if (S6_QREG < S6_LREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(S6_QREG));
         if (bc)
             stream6_riemann<true, MODE, SPH>(A, sm6, RD);
         else
@@ -912,7 +1073,8 @@ int launch_stream6_mode(FusedArgs& A, cudaStream_t stream) {
     if (A.mode == 1)
         return A.f.spherical ? launch_stream6<PPM, 1, true>(A, stream)
                              : launch_stream6<PPM, 1, false>(A, stream);
-    return launch_stream6<PPM, 2, false>(A, stream);
+    return A.f.spherical ? launch_stream6<PPM, 2, true>(A, stream)
+                         : launch_stream6<PPM, 2, false>(A, stream);
 }
 
 #endif

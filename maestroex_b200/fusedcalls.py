@@ -47,3 +47,18 @@ def enthalpy_edge_flux(calls, prob, epar, fpar, outputs=None, stream: int = 0):
             C.c_void_p(stream))
     calls._check(rc, "enthalpy_edge_flux")
     return sedge, sflux
+
+
+def enthalpy_edge_flux_sph(calls, prob, epar, fpar, outputs=None, stream: int = 0):
+    """The spherical form (wdconvect): base state on faces (r0mac / h0mac / rh0mac)."""
+    sedge, sflux, _ = outputs if outputs is not None else prob.clone_outputs()
+    g, st, fo, ep, fp = prob.geom.c(), prob.state.c(), prob.force.c(), epar.c(), fpar.c()
+    m = prob.mac
+    fa = lambda k: fab_array(m[k]) if k in m else None  # noqa: E731
+    fn = calls.lib.mx_enthalpy_edge_flux_sph
+    fn.restype = C.c_int
+    rc = fn(C.byref(g), C.byref(st), fab_array(sedge), fab_array(sflux), fab_array(prob.umac),
+            C.byref(fo), C.byref(ep), fa("r0mac_old"), fa("r0mac_new"), fa("rh0mac_old"),
+            fa("rh0mac_new"), fa("h0mac_old"), fa("h0mac_new"), C.byref(fp), C.c_void_p(stream))
+    calls._check(rc, "enthalpy_edge_flux_sph")
+    return sedge, sflux

@@ -3,11 +3,12 @@
 // order), but MakeEdgeScal(RhoH) + MakeRhoHFlux (Source/MaestroEnthalpyAdvance.cpp:141-146,
 // :229/:312) are ONE library call per box, mx_enthalpy_edge_flux (include/mxadv.h).
 //
-// Supported: 3-D plane-parallel, enthalpy_pred_type = predict_rhoh, predict_rhohprime (the
-// default) or predict_h — the types whose edge state feeds the flux directly.  The
-// temperature-predicting types need HfromRhoTedge (EOS on faces) between the two halves and
-// spherical runs need the h0mac / rhoh0mac face arrays: both abort here (no fallback inside
-// this file; build with the unfused overlay for them).
+// Supported: 3-D, plane-parallel and spherical base state (spherical: mx_enthalpy_edge_flux_sph
+// with the r0mac / rh0mac / h0mac face arrays the reference builds with MakeS0mac, :166-306),
+// enthalpy_pred_type = predict_rhoh, predict_rhohprime (the default) or predict_h — the types
+// whose edge state feeds the flux directly.  The temperature-predicting types need
+// HfromRhoTedge (EOS on faces) between the two halves: they abort here (no fallback inside this
+// file; build with the unfused overlay for them).
 #include <MxadvAmrex.H>
 
 using namespace amrex;
@@ -25,7 +26,6 @@ void Maestro::EnthalpyAdvance(int which_step, Vector<MultiFab>& scalold,
 #if (AMREX_SPACEDIM != 3)
     Abort("libmxadv fused EnthalpyAdvance: 3-D only (use the unfused overlay in 2-D)");
 #endif
-    if (spherical) Abort("libmxadv fused EnthalpyAdvance: plane-parallel only");
     const bool pert = enthalpy_pred_type == predict_rhohprime;
     const bool spec_h = enthalpy_pred_type == predict_h;
     const bool cons = enthalpy_pred_type == predict_rhoh;
@@ -35,12 +35,15 @@ void Maestro::EnthalpyAdvance(int which_step, Vector<MultiFab>& scalold,
     const int nlev = finest_level + 1;
     const int nr1 = base_geom.nr_fine + 1, nrl = base_geom.max_radial_level + 1;
 
+    BaseState<Real> h0_old(nrl, base_geom.nr_fine), h0_new(nrl, base_geom.nr_fine);  // spherical
     BaseState<Real> rho0_edge_old(nrl, nr1), rho0_edge_new(nrl, nr1);
     BaseState<Real> rhoh0_edge_old(nrl, nr1), rhoh0_edge_new(nrl, nr1);
-    CelltoEdge(rho0_old, rho0_edge_old);
-    CelltoEdge(rho0_new, rho0_edge_new);
-    CelltoEdge(rhoh0_old, rhoh0_edge_old);
-    CelltoEdge(rhoh0_new, rhoh0_edge_new);
+    if (!spherical) {
+        CelltoEdge(rho0_old, rho0_edge_old);
+        CelltoEdge(rho0_new, rho0_edge_new);
+        CelltoEdge(rhoh0_old, rhoh0_edge_old);
+        CelltoEdge(rhoh0_new, rhoh0_edge_new);
+    }
 
     if (spec_h) ConvertRhoHToH(scalold, true);
 
@@ -65,6 +68,38 @@ void Maestro::EnthalpyAdvance(int which_step, Vector<MultiFab>& scalold,
     Addw0(umac, w0mac, 1.);
 
     if (pert) PutInPertForm(scalold, rhoh0_old, RhoH, 0, bcs_f, true);
+
+    // spherical: base state on faces, exactly as the reference forms it before MakeRhoHFlux
+    // (Source/MaestroEnthalpyAdvance.cpp:166-306): "old" arrays always, "new" for which_step 2
+    Vector<std::array<MultiFab, AMREX_SPACEDIM> > rho0mac_old(nlev), rhoh0mac_old(nlev), h0mac_old(nlev);
+    Vector<std::array<MultiFab, AMREX_SPACEDIM> > rho0mac_new(nlev), rhoh0mac_new(nlev), h0mac_new(nlev);
+#if (AMREX_SPACEDIM == 3)
+    if (spherical) {
+        auto define3 = [&](Vector<std::array<MultiFab, AMREX_SPACEDIM> >& m) {
+            for (int lev = 0; lev < nlev; ++lev) {
+                m[lev][0].define(convert(grids[lev], nodal_flag_x), dmap[lev], 1, 1);
+                m[lev][1].define(convert(grids[lev], nodal_flag_y), dmap[lev], 1, 1);
+                m[lev][2].define(convert(grids[lev], nodal_flag_z), dmap[lev], 1, 1);
+            }
+        };
+        h0_old.copy(rhoh0_old / rho0_old);
+        define3(rho0mac_old);
+        define3(rhoh0mac_old);
+        define3(h0mac_old);
+        MakeS0mac(rho0_old, rho0mac_old);
+        MakeS0mac(rhoh0_old, rhoh0mac_old);
+        MakeS0mac(h0_old, h0mac_old);
+        if (which_step == 2) {
+            h0_new.copy(rhoh0_new / rho0_new);
+            define3(rho0mac_new);
+            define3(rhoh0mac_new);
+            define3(h0mac_new);
+            MakeS0mac(rho0_new, rho0mac_new);
+            MakeS0mac(rhoh0_new, rhoh0mac_new);
+            MakeS0mac(h0_new, h0mac_new);
+        }
+    }
+#endif
 
     // ---- the fused pass: edge state of the predicted enthalpy quantity + (rho h) flux ------
     {
@@ -94,7 +129,7 @@ void Maestro::EnthalpyAdvance(int which_step, Vector<MultiFab>& scalold,
             MxFluxParams fp;
             fp.species_pred_type = species_pred_type;
             fp.enthalpy_pred_type = enthalpy_pred_type;
-            fp.spherical = 0;
+            fp.spherical = spherical ? 1 : 0;
             fp.use_exact_base_state = use_exact_base_state ? 1 : 0;
             fp.evolve_base_state = evolve_base_state ? 1 : 0;
             fp.rho_comp = Rho;
@@ -111,10 +146,24 @@ void Maestro::EnthalpyAdvance(int which_step, Vector<MultiFab>& scalold,
                 const mxadv::Faces se = mxadv::faces_of(sedge[lev], mfi);
                 const mxadv::Faces sf = mxadv::faces_of(sflux[lev], mfi);
                 const mxadv::Faces um = mxadv::faces_of(umac[lev], mfi);
-                mxadv::check(mx_enthalpy_edge_flux(&g, &st, se.f, sf.f, um.f, &fo, &ep, &b_ro,
-                                                   &b_reo, &b_rn, &b_ren, &b_ho, &b_heo, &b_hn,
-                                                   &b_hen, &fp, mxadv::stream()),
-                             "EnthalpyAdvance (fused edge + flux)");
+                if (spherical) {
+                    const bool two = which_step == 2;
+                    const mxadv::Faces ro = mxadv::faces_of(rho0mac_old[lev], mfi);
+                    const mxadv::Faces rn = mxadv::faces_of(two ? rho0mac_new[lev] : rho0mac_old[lev], mfi);
+                    const mxadv::Faces rho_ = mxadv::faces_of(rhoh0mac_old[lev], mfi);
+                    const mxadv::Faces rhn = mxadv::faces_of(two ? rhoh0mac_new[lev] : rhoh0mac_old[lev], mfi);
+                    const mxadv::Faces ho = mxadv::faces_of(h0mac_old[lev], mfi);
+                    const mxadv::Faces hn = mxadv::faces_of(two ? h0mac_new[lev] : h0mac_old[lev], mfi);
+                    mxadv::check(mx_enthalpy_edge_flux_sph(&g, &st, se.f, sf.f, um.f, &fo, &ep, ro.f,
+                                                           rn.f, rho_.f, rhn.f, ho.f, hn.f, &fp,
+                                                           mxadv::stream()),
+                                 "EnthalpyAdvance (fused edge + flux, spherical)");
+                } else {
+                    mxadv::check(mx_enthalpy_edge_flux(&g, &st, se.f, sf.f, um.f, &fo, &ep, &b_ro,
+                                                       &b_reo, &b_rn, &b_ren, &b_ho, &b_heo, &b_hn,
+                                                       &b_hen, &fp, mxadv::stream()),
+                                 "EnthalpyAdvance (fused edge + flux)");
+                }
             }
         }
         // AMR bookkeeping of MakeRhoHFlux (Source/MaestroMakeFlux.cpp:1040-1066)

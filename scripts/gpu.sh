@@ -47,5 +47,11 @@ case $task in
       bench ${size}_$name MXADV_LIB=$lib -- --size $size --steps 5 --warmup 3 --no-cpu --no-e2e ${BENCH_ARGS:-}
     done
     ;;
+  prof)      # ncu --set full of the density launch: scripts/gpu.sh prof <size> <regex> [env...]
+    size=$1; rx=$2; shift 2
+    env "$@" timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s ${SKIP:-2} -c 1 \
+      -o $out/prof_${tag} -f python bench.py --size $size --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_${tag}.log 2>&1
+    tail -3 $out/ncu_${tag}.log
+    ;;
   *) echo "tasks: k6first | tests | ab <size> <names...>"; exit 2;;
 esac

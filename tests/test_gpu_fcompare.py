@@ -37,21 +37,33 @@ def _table(tmp):
     return dst
 
 
-def _run(exe, rundir, dim, table, extra=()):
+# problem -> (inputs file, initial model, plotfile base name, executable tag, steps)
+PROBLEMS = {
+    "reacting_bubble": (None, "model.hse.cool.coulomb", "plt", "", NSTEPS),
+    # Exec/science/wdconvect, inputs_files/inputs_3d_regression: 64^3, spherical base state,
+    # outflow on all six faces, ppm_type 0 / slope_order 2 as shipped (BASELINE config 3 at
+    # test size; its upstream CI compares 3 steps, .github/workflows/wdconvect-compare.yml)
+    "wdconvect": ("inputs_3d_wdconvect", "kepler_new_6.25e8.hybrid.hse.320", "wdconvect_plt", ".wd", 3),
+}
+
+
+def _run(exe, rundir, dim, table, extra=(), problem="reacting_bubble"):
+    inputs, model, pltbase, _, nsteps = PROBLEMS[problem]
+    inputs = inputs or f"inputs_{dim}d_C"
     os.makedirs(rundir)
-    for f in (f"inputs_{dim}d_C", "model.hse.cool.coulomb"):
+    for f in (inputs, model):
         shutil.copy(os.path.join(E2E, f), rundir)
     os.symlink(table, os.path.join(rundir, "helm_table.dat"))
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = CSRC + ":" + env.get("LD_LIBRARY_PATH", "")
     env.setdefault("OMP_NUM_THREADS", str(min(16, os.cpu_count() or 1)))
-    cmd = [os.path.join(E2E, exe), f"inputs_{dim}d_C", f"maestro.max_step={NSTEPS}",
-           f"maestro.plot_int={NSTEPS}", "maestro.chk_int=-1", "maestro.plot_deltat=-1",
+    cmd = [os.path.join(E2E, exe), inputs, f"maestro.max_step={nsteps}",
+           f"maestro.plot_int={nsteps}", "maestro.chk_int=-1", "maestro.plot_deltat=-1",
            *extra]
     r = subprocess.run(cmd, cwd=rundir, env=env, capture_output=True, text=True, timeout=1500)
     open(os.path.join(rundir, "run.log"), "w").write(r.stdout + r.stderr)
     assert r.returncode == 0, (exe, r.stdout[-2000:], r.stderr[-2000:])
-    plt = os.path.join(rundir, "plt%07d" % NSTEPS)
+    plt = os.path.join(rundir, pltbase + "%07d" % nsteps)
     assert os.path.isdir(plt), os.listdir(rundir)
     return plt, r.stdout
 
@@ -106,3 +118,40 @@ def test_fcompare_10_steps(tmp_path, tmp_path_factory, dim, arm, extra):
     assert len(errs) >= 20, table_txt[-3000:]
     worst = max(errs.items(), key=lambda kv: kv[1][1])
     assert worst[1][1] <= FCOMPARE_TOL, (worst, table_txt[-3000:])
+
+
+@pytest.mark.parametrize("arm,extra", [
+    ("mx", ()),                        # as shipped: ppm_type 0, slope_order 2
+    ("fx", ()),
+    ("fx", ("maestro.ppm_type=1",)),
+    ("mx", ("maestro.ppm_type=2",)),
+])
+def test_fcompare_wdconvect(tmp_path, tmp_path_factory, arm, extra):
+    """BASELINE config 3 as an application: wdconvect (spherical base state, all-outflow) with
+    the overlay on libmxadv.so against the unmodified reference, 3 steps, fcompare <= 1e-10.
+    Exercises Makew0Sphr, the spherical MakeRhoXFlux / MakeRhoHFlux forms (r0mac / h0mac face
+    arrays) and the outflow boundary code of MakeEdgeScal inside the real time step."""
+    for f in ("Maestro3d.wd.ref.ex", f"Maestro3d.wd.{arm}.ex", "fcompare3d.ex", "helm_table.dat.gz",
+              "inputs_3d_wdconvect"):
+        if not os.path.exists(os.path.join(E2E, f)):
+            pytest.skip(f"oracle/_ref/e2e/{f} not built (oracle/e2e/build_e2e.sh 3 wdconvect)")
+    if "table" not in _CACHE:
+        _CACHE["table"] = _table(str(tmp_path_factory.mktemp("helm")))
+    table = _CACHE["table"]
+    key = ("wd", extra)
+    if key not in _CACHE:
+        rdir = os.path.join(str(tmp_path_factory.mktemp("wdref")), "ref")
+        _CACHE[key] = _run("Maestro3d.wd.ref.ex", rdir, 3, table, extra, problem="wdconvect")[0]
+    pm, _ = _run(f"Maestro3d.wd.{arm}.ex", os.path.join(str(tmp_path), arm), 3, table, extra,
+                 problem="wdconvect")
+    r = subprocess.run([os.path.join(E2E, "fcompare3d.ex"), "-a", _CACHE[key], pm],
+                       capture_output=True, text=True, timeout=600)
+    keep = os.environ.get("MXADV_FCOMPARE_OUT")
+    if keep:
+        os.makedirs(keep, exist_ok=True)
+        tag = "wdconvect_" + arm + "".join("_" + e.split(".")[-1] for e in extra)
+        open(os.path.join(keep, f"fcompare_{tag}.txt"), "w").write(r.stdout + r.stderr)
+    errs = parse_fcompare(r.stdout)
+    assert len(errs) >= 20, r.stdout[-3000:]
+    worst = max(errs.items(), key=lambda kv: kv[1][1])
+    assert worst[1][1] <= FCOMPARE_TOL, (worst, r.stdout[-3000:])
