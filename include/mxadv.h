@@ -144,9 +144,10 @@ int mx_device_count(void);
 /* Number of kernels this library has launched since load (or since mx_reset_launch_count). */
 long long mx_launch_count(void);
 void mx_reset_launch_count(void);
-/* How many of those were the TMA-fed, role-specialised streaming kernel (k_stream6); the
- * remainder of the fused launches ran the cp.async kernel (k_stream4: fabs whose rows are an
- * odd number of doubles or whose base is not 16-byte aligned cannot be described to TMA). */
+/* How many of those were the TMA-fed instantiation of the streaming kernel k_stream4 (scalar
+ * planes staged by cp.async.bulk.tensor); the remainder of the fused launches ran its cp.async
+ * instantiation (fabs whose rows are an odd number of doubles or whose base is not 16-byte
+ * aligned cannot be described to TMA). */
 long long mx_tma_launch_count(void);
 /* Release the cached device workspaces. */
 int mx_free_workspace(void);

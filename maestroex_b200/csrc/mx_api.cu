@@ -748,7 +748,7 @@ int mx_density_edge_flux(const MxGeom* geom, const MxFab* state, const MxFab* se
     const KEdge e = make_kedge(epar);
     // host fabs: copy and compute slab by slab (Session::run_slabs)
     if (!sph && fused_density_supported(kg, e, f) && !is_device_ptr(state->p) &&
-        kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE") && !getenv("MXADV_KERNEL"))
+        kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE"))
         S.defer_copies();
     MX_TRY(check_cover(geom, state, ng_s, -1, "state"));
     MX_TRY(check_cover(geom, force, 1, -1, "force"));
@@ -861,7 +861,7 @@ static int enthalpy_edge_flux_impl(const MxGeom* geom, const MxFab* state, const
     const KGeom kg = make_kgeom(geom);
     const KEdge e = make_kedge(epar);
     if (!sph && fused_enthalpy_supported(kg, e, f) && !is_device_ptr(state->p) &&
-        kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE") && !getenv("MXADV_KERNEL"))
+        kg.vhi[2] - kg.vlo[2] + 1 >= 32 && !getenv("MXADV_NO_PIPELINE"))
         S.defer_copies();
     EdgeArgs a;
     MX_TRY(stage_edge_args(S, geom, state, sedge, umac, force, epar, &a));

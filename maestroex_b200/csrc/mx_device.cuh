@@ -29,61 +29,17 @@ constexpr int BC_HOEXTRAP = 4;
 MXD double dmin_(double a, double b) { return (b < a) ? b : a; }
 MXD double dmax_(double a, double b) { return (a < b) ? b : a; }
 
-// ---------------------------------------------------------------------------------------
-// Two independent values processed in lock step.  The reconstruction role of k_stream6 runs ONE
-// warp per SM sub-partition, so its speed is set by dependent-issue latency (8 cycles per fp64
-// operation); writing the arithmetic over pairs (two tile rows at once) puts a second,
-// independent instruction next to every instruction of the chain.  Every device function below
-// that the parabolic reconstruction uses is generic over T = double or D2: the pair version is
-// the scalar expression tree applied to both halves, hence bit-identical.
-// ---------------------------------------------------------------------------------------
-struct D2 {
-    double a, b;
-};
-struct B2 {
-    bool a, b;
-};
-MXD D2 d2(double a, double b) { return D2{a, b}; }
-MXD D2 d2(double a) { return D2{a, a}; }
-MXD D2 operator+(D2 x, D2 y) { return D2{x.a + y.a, x.b + y.b}; }
-MXD D2 operator-(D2 x, D2 y) { return D2{x.a - y.a, x.b - y.b}; }
-MXD D2 operator*(D2 x, D2 y) { return D2{x.a * y.a, x.b * y.b}; }
-MXD D2 operator-(D2 x) { return D2{-x.a, -x.b}; }
-MXD D2 operator*(double s, D2 x) { return D2{s * x.a, s * x.b}; }
-MXD D2 operator*(D2 x, double s) { return D2{x.a * s, x.b * s}; }
-MXD D2 operator+(double s, D2 x) { return D2{s + x.a, s + x.b}; }
-MXD D2 operator-(double s, D2 x) { return D2{s - x.a, s - x.b}; }
-MXD D2 operator+(D2 x, double s) { return D2{x.a + s, x.b + s}; }
-MXD D2 operator-(D2 x, double s) { return D2{x.a - s, x.b - s}; }
-MXD B2 operator<(D2 x, D2 y) { return B2{x.a < y.a, x.b < y.b}; }
-MXD B2 operator>(D2 x, D2 y) { return B2{x.a > y.a, x.b > y.b}; }
-MXD B2 operator<=(D2 x, D2 y) { return B2{x.a <= y.a, x.b <= y.b}; }
-MXD B2 operator>=(D2 x, D2 y) { return B2{x.a >= y.a, x.b >= y.b}; }
-MXD B2 operator<(D2 x, double y) { return B2{x.a < y, x.b < y}; }
-MXD B2 operator>(D2 x, double y) { return B2{x.a > y, x.b > y}; }
-MXD B2 operator<=(D2 x, double y) { return B2{x.a <= y, x.b <= y}; }
-MXD B2 operator>=(D2 x, double y) { return B2{x.a >= y, x.b >= y}; }
-MXD B2 operator!(B2 m) { return B2{!m.a, !m.b}; }
-MXD B2 operator&&(B2 m, B2 n) { return B2{m.a && n.a, m.b && n.b}; }
-// select
+// select / fused multiply-add / multiply spelled as functions so that the reconstruction
+// templates below read the same for any value type
 MXD double sel(bool m, double x, double y) { return m ? x : y; }
-MXD D2 sel(B2 m, D2 x, D2 y) { return D2{m.a ? x.a : y.a, m.b ? x.b : y.b}; }
-MXD D2 sel(B2 m, double x, double y) { return D2{m.a ? x : y, m.b ? x : y}; }
-MXD D2 dmin_(D2 a, D2 b) { return D2{dmin_(a.a, b.a), dmin_(a.b, b.b)}; }
-MXD D2 dmax_(D2 a, D2 b) { return D2{dmax_(a.a, b.a), dmax_(a.b, b.b)}; }
-MXD D2 fma_(D2 x, D2 y, D2 z) { return D2{__fma_rn(x.a, y.a, z.a), __fma_rn(x.b, y.b, z.b)}; }
-MXD D2 fma_(double x, D2 y, D2 z) { return D2{__fma_rn(x, y.a, z.a), __fma_rn(x, y.b, z.b)}; }
-MXD D2 fma_(D2 x, double y, D2 z) { return D2{__fma_rn(x.a, y, z.a), __fma_rn(x.b, y, z.b)}; }
 MXD double fma_(double x, double y, double z) { return __fma_rn(x, y, z); }
 MXD double mul_(double x, double y) { return __dmul_rn(x, y); }
-MXD D2 mul_(D2 x, double y) { return D2{__dmul_rn(x.a, y), __dmul_rn(x.b, y)}; }
 
 // copysign(1.0, sgn) * mag for mag >= +0 (exact: +-1 * mag only flips the sign bit)
 MXD double signed_mag(double mag, double sgn) {
     return __hiloint2double((__double2hiint(mag) & 0x7fffffff) | (__double2hiint(sgn) & 0x80000000),
                             __double2loint(mag));
 }
-MXD D2 signed_mag(D2 mag, D2 sgn) { return D2{signed_mag(mag.a, sgn.a), signed_mag(mag.b, sgn.b)}; }
 MXD double sign1(double sgn) { return signed_mag(1.0, sgn); }
 
 // (prod > 0.0) ? r : +0.0 as a select.  Written in PTX because nvcc otherwise sinks the
@@ -98,7 +54,6 @@ MXD double sel_pos(double prod, double r) {
     return out;
 }
 
-MXD D2 sel_pos(D2 prod, D2 r) { return D2{sel_pos(prod.a, r.a), sel_pos(prod.b, r.b)}; }
 
 // Correctly rounded x / c for the compile-time constants c = 6 and c = 3 (Markstein-style:
 // q0 = RN(x * RN(1/c)), r = x - c*q0 exactly via FMA, q = RN(q0 + r * RN(1/c))).  Verified
@@ -237,7 +192,6 @@ MXD double slope_any(int order, const double* S, int I, int lo, int hi, bool lob
 MXD double abs_(double x) {
     return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
 }
-MXD D2 abs_(D2 x) { return D2{abs_(x.a), abs_(x.b)}; }
 
 // van Leer slope (MaestroPPM.cpp:42-49): with dsc = (sp1 - sm1)/2, dsl = 2 (s0 - sm1),
 // dsr = 2 (sp1 - s0) the reference forms sign(dsc) min(|dsc|, |dsl|, |dsr|) if dsl dsr > 0, else 0.
@@ -296,7 +250,6 @@ MXD T bc_edge(T a, T b, T c, T d, T m0, T m1) {
 
 // ppm_type 1, second half: CW84 limiter + BC rows applied to the unlimited edge values
 // sm_u = edge(i-1/2), sp_u = edge(i+1/2) (MaestroPPM.cpp:100-205).  S[o+3], o in [-2,2] read.
-// (T = D2: both halves sit at the same index I along the sweep direction.)
 template <bool BC, class T>
 MXD void ppm1_finish(const T* S, int I, int lo, int hi, bool lobc, bool hibc, T sm_u, T sp_u,
                      T& sm, T& sp) {

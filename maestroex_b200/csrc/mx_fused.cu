@@ -69,7 +69,7 @@ struct FusedArgs {
     int nzc;           // number of z chunks
     int ntx, nty;  // number of tiles
     int bcdir[3];  // some swept component has a non-interior BC in this direction
-    alignas(64) CUtensorMap tmap_state;  // k_stream6: (x, y, z, comp) view of `state` for TMA
+    alignas(64) CUtensorMap tmap_state;  // (x, y, z, comp) view of `state` for the TMA ring fill
 };
 
 // z range [k0, k1) of chunk c.  Where a swept component has a physical BC on a vertical domain
@@ -95,7 +95,6 @@ __device__ __forceinline__ void chunk_range(const FusedArgs& A, int c, int& k0, 
 
 #include "mx_stream.cuh"
 #include "mx_stream4.cuh"
-#include "mx_stream6.cuh"
 
 // chunking of the z range (see chunk_range): short boundary chunks only for k_stream4/5.
 // Unless MXADV_ZCHUNK fixes it, the chunk length is chosen by simulating the block schedule
@@ -178,16 +177,6 @@ int dispatch(FusedArgs& A, int ppm_type, cudaStream_t stream) {
     A.nty = (ny + (S4_GY - 2) - 1) / (S4_GY - 2);
     if (A.zc > ST_MAXZC) A.zc = ST_MAXZC;
     set_zchunks(A, true);
-    // k_stream6 (role-specialised, TMA) unless the box cannot take TMA or MXADV_KERNEL=v4 asks
-    // for the previous kernel (A/B runs)
-    const char* kv = getenv("MXADV_KERNEL");
-    if (!(kv && kv[0] == 'v' && kv[1] == '4')) {
-        const int r = ppm_type == 0   ? launch_stream6_mode<0>(A, stream)
-                      : ppm_type == 1 ? launch_stream6_mode<1>(A, stream)
-                                      : launch_stream6_mode<2>(A, stream);
-        if (r <= 0) return r;
-    }
-    if (A.mode == 2 && A.f.spherical) return 1;  // k_stream4 has no spherical enthalpy form
     if (ppm_type == 0) return launch_stream4_mode<0>(A, stream);
     if (ppm_type == 1) return launch_stream4_mode<1>(A, stream);
     return launch_stream4_mode<2>(A, stream);

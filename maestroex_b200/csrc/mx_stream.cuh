@@ -6,7 +6,6 @@
 
 MXD double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 MXD double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-MXD D2 shfl_dn1(D2 v) { return D2{shfl_dn1(v.a), shfl_dn1(v.b)}; }
 
 MXD void cp_async8(double* dst_smem, const double* src, bool pred) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -19,6 +18,37 @@ template <int N>
 MXD void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// ---- TMA / mbarrier (sm_90+) -------------------------------------------------------------
+MXD unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+MXD void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+MXD void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+                 : "memory");
+}
+MXD void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MX_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MX_DONE_%=;\n\t"
+        "bra MX_WAIT_%=;\n\t"
+        "MX_DONE_%=:\n\t}" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+// one box {PW, PH, 1, 1} of the state fab (x, y, z, component) -> shared memory; completion is
+// signalled on `bar` (complete_tx of the box's bytes); out-of-range elements arrive as zeros
+MXD void tma_load_plane(double* dst, const void* tmap, unsigned long long* bar, int c0, int c1,
+                        int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 MXD void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 MXD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 

@@ -1,6 +1,6 @@
 // mx_stream4.cuh — k_stream4: the streaming edge-state (+flux) kernel, fourth revision.
-// Same decomposition, phases and arithmetic as k_stream (mx_stream.cuh, kept for A/B runs
-// with MXADV_KERNEL=v3); what changed is everything *around* the arithmetic, which the
+// Same decomposition, phases and arithmetic as the first streaming kernel of round 1 (k_stream,
+// since removed); what changed is everything *around* the arithmetic, which the
 // round-1 ncu capture showed to be ~60 % of the issued instructions
 // (profiles/r1a_k_stream_v3_ncu_full_n256.txt):
 //   * every global array is addressed through a per-thread running pointer that advances by
@@ -12,6 +12,13 @@
 //     loaded into registers two phases ahead instead of being prefetched into L1;
 //   * the z stencil is read from an 8-slot shared-memory ring (planes a-LA .. a+LA resident,
 //     a+LA+1 in flight) instead of a register window that was shifted every plane.
+// Round 2: the ring is filled by TMA (template flag TMA): one elected thread issues one
+// cp.async.bulk.tensor per plane from a 4-D tensor map (x, y, z, component) over the caller's
+// ghost-grown state fab, completion is tracked by one mbarrier per ring slot, and the hardware
+// zero-fills whatever lies outside the fab.  The per-thread staging plan of the cp.async
+// version (two source pointers, two offsets, four predicates per thread) disappears.  TMA needs
+// a 16-byte aligned base and 16-byte multiples as global strides, i.e. an even number of
+// doubles per fab row (every BASELINE configuration); other boxes keep the cp.async version.
 #ifndef MX_STREAM4_CUH
 #define MX_STREAM4_CUH
 
@@ -24,19 +31,25 @@ constexpr int S4_NS = 8;  // ring slots (power of two)
 #define S4_MINB 1
 #endif
 
+// doubles per ring slot: a 128-byte multiple (TMA destination alignment)
 template <int PPM>
-constexpr int stream4_smem_doubles() {
+__host__ __device__ constexpr int s4_pls() {
     constexpr int LA = (PPM == 2) ? 3 : 2;
-    return S4_NS * (32 + 2 * LA) * (S4_GY + 2 * LA) + 9 * (32 * S4_GY + 64) + 16 * (32 * S4_GY) +
-           5 * (ST_MAXZC + 2);
+    return ((32 + 2 * LA) * (S4_GY + 2 * LA) + 15) & ~15;
+}
+template <int PPM>
+__host__ __device__ constexpr int stream4_smem_doubles() {
+    return S4_NS * s4_pls<PPM>() + 9 * (32 * S4_GY + 64) + 16 * (32 * S4_GY) + 5 * (ST_MAXZC + 2) + 2 +
+           S4_NS;  // + the mbarriers of the ring slots (8-byte aligned: every term before is even)
 }
 
-template <int PPM, bool BC, int MODE, bool SPH>
+template <int PPM, bool BC, int MODE, bool SPH, bool TMA>
 __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     constexpr int GX = 32, GY = S4_GY;
     constexpr int LA = (PPM == 2) ? 3 : 2;  // stencil radius
     constexpr int PW = GX + 2 * LA, PH = GY + 2 * LA;
-    constexpr int PL = PW * PH;  // doubles per ring plane
+    constexpr int PL = PW * PH;       // doubles per staged plane
+    constexpr int PLS = s4_pls<PPM>();  // ring slot pitch
     constexpr int NT = GX * GY;
     constexpr int BX = GX - 2, BY = GY - 2;
     constexpr int NLD = (PL + NT - 1) / NT;
@@ -46,7 +59,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     // outermost tile rows read "their neighbour" there (their y-direction results are never
     // stored), so no thread ever reads a slot another thread writes without a barrier between
     constexpr int XS = NT + 2 * GX;
-    double* ex = ring + S4_NS * PL + GX;
+    double* ex = ring + S4_NS * PLS + GX;
     double* X_IPY = ex + 0 * XS;
     double* X_SY = ex + 1 * XS;
     double* X_T6X = ex + 2 * XS;
@@ -63,6 +76,8 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     double* T_W0R = tab + 2 * (ST_MAXZC + 2);  // w0(a) * rho0_predicted_edge(a)
     double* T_HXY = tab + 3 * (ST_MAXZC + 2);  // 0.5 (rhoh0_old + rhoh0_new)(p)
     double* T_HZ = tab + 4 * (ST_MAXZC + 2);   // 0.5 (rhoh0_edge_old + _new)(a)
+    unsigned long long* const mbar =
+        reinterpret_cast<unsigned long long*>(tab + 5 * (ST_MAXZC + 2) + 2);  // one per ring slot (TMA)
 
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
@@ -149,15 +164,21 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     // cp.async staging plan of this thread: element e = tid + q*NT of a PW x PH plane
     long ld_off[NLD];
     bool ld_do[NLD], ld_in[NLD];
+    if (!TMA) {
 #pragma unroll
-    for (int q = 0; q < NLD; ++q) {
-        const int e = tid + q * NT;
-        const int px = e % PW, py = e / PW;
-        const int gi = x0 - 1 - LA + px - st.lo[0], gj = y0 - 1 - LA + py - st.lo[1];
-        ld_do[q] = e < PL;
-        ld_in[q] = ld_do[q] && gi >= 0 && gi < st.n[0] && gj >= 0 && gj < st.n[1];
-        ld_off[q] = ld_in[q] ? (long)gj * st.sy + gi : 0;
+        for (int q = 0; q < NLD; ++q) {
+            const int e = tid + q * NT;
+            const int px = e % PW, py = e / PW;
+            const int gi = x0 - 1 - LA + px - st.lo[0], gj = y0 - 1 - LA + py - st.lo[1];
+            ld_do[q] = e < PL;
+            ld_in[q] = ld_do[q] && gi >= 0 && gi < st.n[0] && gj >= 0 && gj < st.n[1];
+            ld_off[q] = ld_in[q] ? (long)gj * st.sy + gi : 0;
+        }
     }
+    // TMA: tile origin in the fab's own coordinates (may lie outside: zero fill), per-slot
+    // parity of the next wait (every thread waits for every plane exactly once)
+    const int cx0 = x0 - 1 - LA - st.lo[0], cy0 = y0 - 1 - LA - st.lo[1], cz0 = a0 - LA - st.lo[2];
+    unsigned phase = 0;
 
     const double c6x = A.c6h[0], c6y = A.c6h[1], c6z = A.c6h[2];
     const double c4x = A.c4h[0], c4y = A.c4h[1], c4z = A.c4h[2];
@@ -165,7 +186,9 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     // flux-form switches (block uniform)
     const bool have_h = (MODE == 2) && (F_.ept == MX_PRED_H || F_.ept == MX_PRED_T_THEN_H ||
                                         F_.ept == MX_PRED_TPRIME_THEN_H);
-    const bool need_ser = (MODE == 1) ? (F_.spt != MX_PRED_RHOX) : have_h;
+    // sedge(Rho) is an input of the flux: species forms except (rho X); h forms; spherical h'
+    const bool need_ser = (MODE == 1) ? (F_.spt != MX_PRED_RHOX)
+                                      : (have_h || (sph && F_.ept == MX_PRED_HPRIME));
 
     // velocity / force columns are component independent
     const long u_c = A.umac[0].off(il, jl, a0), v_c = A.umac[1].off(il, jl, a0);
@@ -215,6 +238,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
         double* __restrict__ pEta = nullptr;
         long dRx = 0, dRy = 0, dRz = 0, dGx = 0, dGy = 0, dGz = 0;  // rho comp - this comp
         long dQx = 0, dQy = 0, dQz = 0;  // spherical: r0e - this comp of sedge
+        long dHx = 0, dHy = 0, dHz = 0;  // spherical enthalpy pass: h0e - this comp of sedge
         if (MODE != 0) {
             pFx = A.sflux[0].comp(comp) + fx_c;
             pFy = A.sflux[1].comp(comp) + fy_c;
@@ -233,27 +257,49 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                 dGz = (long)(F_.rho - comp) * A.sflux[2].sn;
                 if (A.do_eta) pEta = A.eta.p + eta_c;
             }
+            if (MODE == 2 && sph) {
+                dQx = A.r0e[0] - A.sedge[0].comp(comp);
+                dQy = A.r0e[1] - A.sedge[1].comp(comp);
+                dQz = A.r0e[2] - A.sedge[2].comp(comp);
+                dHx = A.h0e[0] - A.sedge[0].comp(comp);
+                dHy = A.h0e[1] - A.sedge[1].comp(comp);
+                dHz = A.h0e[2] - A.sedge[2].comp(comp);
+            }
         }
         const double* __restrict__ pS[NLD];  // source of ring element q, plane being staged
-        {
+        if (!TMA) {
             const double* sp_ = st.comp(comp) + (long)(a0 - LA - st.lo[2]) * st_sz;
 #pragma unroll
             for (int q = 0; q < NLD; ++q) pS[q] = sp_ + ld_off[q];
         }
-        auto stage_plane = [&](int slot) {
-            double* dst = ring + slot * PL + tid;
+        // stage plane number q of this component's sweep (plane a0 - LA + q) into its ring slot
+        auto stage_plane = [&](int q_) {
+            const int slot = q_ & (S4_NS - 1);
+            if (TMA) {
+                if (tid == 0) {
+                    mbar_expect_tx(mbar + slot, PL * 8);
+                    tma_load_plane(ring + slot * PLS, &A.tmap_state, mbar + slot, cx0, cy0, cz0 + q_, comp);
+                }
+            } else {
+                double* dst = ring + slot * PLS + tid;
 #pragma unroll
-            for (int q = 0; q < NLD; ++q) {
-                if (ld_do[q]) cp_async8(dst + q * NT, pS[q], ld_in[q]);
-                pS[q] += st_sz;
+                for (int q = 0; q < NLD; ++q) {
+                    if (ld_do[q]) cp_async8(dst + q * NT, pS[q], ld_in[q]);
+                    pS[q] += st_sz;
+                }
             }
+        };
+        auto wait_plane = [&](int q_) {  // TMA only: plane q_ has landed (acquire for this thread)
+            const int slot = q_ & (S4_NS - 1);
+            mbar_wait(mbar + slot, (phase >> slot) & 1u);
+            phase ^= 1u << slot;
         };
 
         // ---- prologue ---------------------------------------------------------------
         __syncthreads();  // previous component is done with shared memory; tables written
 #pragma unroll
         for (int q = 0; q <= 2 * LA; ++q) stage_plane(q);  // planes a0-LA .. a0+LA
-        cp_async_commit();
+        if (!TMA) cp_async_commit();
         // register prefetch of plane a0
         double w_m1 = 0.0, w_0 = 0.0;
         double w_p1 = pW[-w_sz];  // face a0
@@ -270,19 +316,24 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
 #pragma unroll
         for (int v = 0; v < 16; ++v) HS(v) = 0.0;
         bool slow_p = true;
-        cp_async_wait<0>();
+        if (TMA) {
+#pragma unroll
+            for (int q = 0; q <= 2 * LA; ++q) wait_plane(q);
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();  // planes a0-LA .. a0+LA are in the ring
         {
             // incremental z reconstruction state from planes a0-2 .. a0+1
             const double* c = ring + rc;
             if (PPM == 1) {
-                const double zm2 = c[(LA - 2) * PL], zm1 = c[(LA - 1) * PL], z0 = c[LA * PL],
-                             zp1 = c[(LA + 1) * PL];
+                const double zm2 = c[(LA - 2) * PLS], zm1 = c[(LA - 1) * PLS], z0 = c[LA * PLS],
+                             zp1 = c[(LA + 1) * PLS];
                 const double dm1 = vanleer(zm2, zm1, z0);
                 dz_c = vanleer(zm1, z0, zp1);
                 ez_lo = vl_edge(zm1, z0, dm1, dz_c);
             } else if (PPM == 2) {
-                const double z[6] = {c[0], c[PL], c[2 * PL], c[3 * PL], c[4 * PL], c[5 * PL]};
+                const double z[6] = {c[0], c[PLS], c[2 * PLS], c[3 * PLS], c[4 * PLS], c[5 * PLS]};
                 ez_l2 = cs_edge(z[0], z[1], z[2], z[3]);
                 ez_l1 = cs_edge(z[1], z[2], z[3], z[4]);
                 ez_h1 = cs_edge(z[2], z[3], z[4], z[5]);
@@ -293,7 +344,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             const int it = a - a0;
             const bool bcz = bcz_c && ((a <= g.dlo[2] + 4) || (a >= g.dhi[2] - 4));  // block uniform
             const bool lobcz = lobcz_c && bcz, hibcz = hibcz_c && bcz;
-            const double* pa = ring + ((it + LA) & (S4_NS - 1)) * PL + rc;  // plane a, my cell
+            const double* pa = ring + ((it + LA) & (S4_NS - 1)) * PLS + rc;  // plane a, my cell
             // ---- P0: current-plane registers, prefetch of the next plane ----------------
 #ifdef MX_EXP_FAKEIN
             // experiment (wrong results): velocities / force read from a shared-memory plane as a
@@ -304,7 +355,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             w_m1 = fk[(tid & 31) + 3];
             w_0 = fk[(tid & 31) + 4];
             w_p1 = fk[(tid & 31) + 5];
-            if (a < k1) stage_plane((it + 2 * LA + 1) & (S4_NS - 1));
+            if (a < k1) stage_plane(it + 2 * LA + 1);
             if (false) {
 #else
             const double um = um_n, vm = vm_n, vp = vp_n, f0 = f_n;
@@ -314,7 +365,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             w_0 = w_p1;
             w_p1 = w_n;
             if (a < k1) {  // block uniform
-                stage_plane((it + 2 * LA + 1) & (S4_NS - 1));  // plane a+LA+1
+                stage_plane(it + 2 * LA + 1);  // plane a+LA+1
 #endif
                 pU += u_sz;
                 pV += v_sz;
@@ -327,7 +378,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                 w_n = pW[0];
                 f_n = pF[0];
             }
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
             // velocity predicates of this plane's faces
             const bool px_pos = um > 0.0, px_nz0 = fabs(um) > 0.0, px_nz = fabs(um) > eps;
             const bool py_pos = vm > 0.0, py_nz0 = fabs(vm) > 0.0, py_nz = fabs(vm) > eps;
@@ -383,8 +434,12 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             }
             X_IPY[tid] = ipy;
             if (PPM != 0) X_SY[tid] = imy;  // right state of my low y face, for the row below
-            cp_async_wait<1>();  // this thread's share of plane a+LA has landed
-            __syncthreads();     // S2: publishes IPY and ring plane a+LA
+            if (TMA) {
+                if (it > 0) wait_plane(it + 2 * LA);  // plane a+LA has landed (it == 0: prologue)
+            } else {
+                cp_async_wait<1>();  // this thread's share of plane a+LA has landed
+            }
+            __syncthreads();  // S2: publishes IPY (and, cp.async, ring plane a+LA)
 
             // ---- P2: z reconstruction, 1-D states, first Riemann solve -------------------
             double ipz, imz, s_zm1 = 0.0;
@@ -396,7 +451,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                 for (int q = -LA; q <= LA; ++q) {
                     const bool need = (BC && bcz) || PPM != 1 || q > 0;
                     S[q + 3] = (q == 0) ? s0
-                               : need   ? ring[((it + LA + q) & (S4_NS - 1)) * PL + rc]
+                               : need   ? ring[((it + LA + q) & (S4_NS - 1)) * PLS + rc]
                                         : 0.0;
                 }
                 if (PPM == 0) {
@@ -503,7 +558,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                     if (do_z) g_z = pFz[dGz];
                 }
                 if (MODE == 1 && A.do_eta && do_z) e_z = pEta[0];
-                if (MODE == 1 && sph) {  // time-centred rho0 on this face (mac_average output)
+                if (sph) {  // time-centred base state on this face (mac_average output)
                     if (do_xy) {
                         q_x = pEx[dQx];
                         q_y = pEy[dQy];
@@ -605,6 +660,13 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                         pFy[0] = fly;
                         pFy[dGy] = g_y + fly;
                     }
+                } else if (MODE == 2 && sph) {
+                    // MakeRhoHFlux (spherical), MaestroMakeFlux.cpp:871-1021
+                    double fl;
+                    if (rhoh_flux_sph(F_, uf_p, r_x, ex_v, q_x, pEx[dHx], &fl))
+                        if (ownx) pFx[0] = fl;
+                    if (rhoh_flux_sph(F_, vf_p, r_y, ey_v, q_y, pEy[dHy], &fl))
+                        if (owny) pFy[0] = fl;
                 } else if (MODE == 2) {
                     // MakeRhoHFlux (planar), MaestroMakeFlux.cpp:674-786
                     double fl;
@@ -639,6 +701,10 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                         if (last_spec) ev -= T_W0R[it];
                         if (ownz) pEta[0] = ev;
                     }
+                } else if (MODE == 2 && sph) {
+                    double fl;
+                    if (rhoh_flux_sph(F_, w_0, r_z, ez_v, q_z, pEz[dHz], &fl))
+                        if (ownz) pFz[0] = fl;
                 } else if (MODE == 2) {
                     double fl;
                     if (rhoh_flux_tab(F_, have_h, w_0, r_z, ez_v, T_RZ[it], T_HZ[it], true, &fl))
@@ -672,14 +738,14 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             HS(H_FS) = fs_cur;
             slow_p = slow_c;
         }
-        cp_async_wait<0>();
+        if (!TMA) cp_async_wait<0>();
     }
 #undef HS
 }
 
-template <int PPM, int MODE, bool SPH>
+template <int PPM, int MODE, bool SPH, bool TMA>
 __global__ void __launch_bounds__(32 * S4_GY, S4_MINB) k_stream4(const __grid_constant__ FusedArgs A) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) double sm[];
     // physical-boundary code only in blocks whose (grown) tile reaches a domain face that has
     // a non-interior BC; everything else runs the BC-free instantiation
     constexpr int BX = 30, BY = S4_GY - 2;
@@ -692,13 +758,63 @@ __global__ void __launch_bounds__(32 * S4_GY, S4_MINB) k_stream4(const __grid_co
     if (A.bcdir[0]) bc |= (x0 - 1 <= g.dlo[0] + 2) || (x0 + BX >= g.dhi[0] - 2);
     if (A.bcdir[1]) bc |= (y0 - 1 <= g.dlo[1] + 2) || (y0 + BY >= g.dhi[1] - 2);
     if (A.bcdir[2]) bc |= (k0 - 1 <= g.dlo[2] + 2) || (k1 >= g.dhi[2] - 2);
+    if (TMA && threadIdx.x == 0) {
+        // one mbarrier per ring slot; the body's first __syncthreads publishes them
+        unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(
+            sm + stream4_smem_doubles<PPM>() - S4_NS);
+#pragma unroll
+        for (int q = 0; q < S4_NS; ++q) mbar_init(mbar + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (bc)
-        stream4_body<PPM, true, MODE, SPH>(A, sm);
+        stream4_body<PPM, true, MODE, SPH, TMA>(A, sm);
     else
-        stream4_body<PPM, false, MODE, SPH>(A, sm);
+        stream4_body<PPM, false, MODE, SPH, TMA>(A, sm);
 }
 
-template <int PPM, int MODE, bool SPH>
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+// 4-D tensor map (x, y, z, component) over the caller's ghost-grown state fab, box = one staged
+// plane {PW, PH, 1, 1}.  cuTensorMapEncodeTiled is fetched through the runtime's driver entry
+// point query, so libmxadv.so does not link libcuda.
+typedef CUresult (*mx_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                       const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline mx_encode_tiled_fn encode_tiled() {
+    static std::atomic<void*> fn{nullptr};
+    void* f = fn.load(std::memory_order_acquire);
+    if (f == nullptr) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn.store(f, std::memory_order_release);
+    }
+    return reinterpret_cast<mx_encode_tiled_fn>(f);
+}
+
+// false: this box cannot take TMA (odd fab rows / unaligned base / no driver entry point)
+template <int PPM>
+bool stream4_tmap(FusedArgs& A) {
+    constexpr int LA = (PPM == 2) ? 3 : 2;
+    const DFab& st = A.state;
+    if ((reinterpret_cast<uintptr_t>(st.p) & 15u) != 0 || (st.n[0] & 1) != 0) return false;
+    mx_encode_tiled_fn enc = encode_tiled();
+    if (enc == nullptr) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)st.n[0], (cuuint64_t)st.n[1], (cuuint64_t)st.n[2],
+                                (cuuint64_t)st.ncomp};
+    const cuuint64_t strides[3] = {(cuuint64_t)st.sy * 8, (cuuint64_t)st.sz * 8, (cuuint64_t)st.sn * 8};
+    const cuuint32_t box[4] = {32 + 2 * LA, S4_GY + 2 * LA, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(&A.tmap_state, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, st.p, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int PPM, int MODE, bool SPH, bool TMA>
 int launch_stream4(const FusedArgs& A, cudaStream_t stream) {
     const size_t smem = sizeof(double) * (size_t)stream4_smem_doubles<PPM>();
     // cudaFuncSetAttribute is per device: remember which devices have it (bit d of the mask)
@@ -707,24 +823,33 @@ int launch_stream4(const FusedArgs& A, cudaStream_t stream) {
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & bit)) {
-        if (cudaFuncSetAttribute(k_stream4<PPM, MODE, SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_stream4<PPM, MODE, SPH, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
         attr_set.fetch_or(bit, std::memory_order_relaxed);
     }
     dim3 grid(A.ntx * A.nty, A.nzc);
-    k_stream4<PPM, MODE, SPH><<<grid, 32 * S4_GY, smem, stream>>>(A);
+    k_stream4<PPM, MODE, SPH, TMA><<<grid, 32 * S4_GY, smem, stream>>>(A);
     mx_count_launch();
+    if (TMA) mx_count_tma_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-template <int PPM>
-int launch_stream4_mode(const FusedArgs& A, cudaStream_t stream) {
-    if (A.mode == 0) return launch_stream4<PPM, 0, false>(A, stream);
+template <int PPM, bool TMA>
+int launch_stream4_tma(const FusedArgs& A, cudaStream_t stream) {
+    if (A.mode == 0) return launch_stream4<PPM, 0, false, TMA>(A, stream);
     if (A.mode == 1)
-        return A.f.spherical ? launch_stream4<PPM, 1, true>(A, stream)
-                             : launch_stream4<PPM, 1, false>(A, stream);
-    return launch_stream4<PPM, 2, false>(A, stream);
+        return A.f.spherical ? launch_stream4<PPM, 1, true, TMA>(A, stream)
+                             : launch_stream4<PPM, 1, false, TMA>(A, stream);
+    return A.f.spherical ? launch_stream4<PPM, 2, true, TMA>(A, stream)
+                         : launch_stream4<PPM, 2, false, TMA>(A, stream);
+}
+
+// MXADV_NO_TMA=1 forces the cp.async staging (A/B runs)
+template <int PPM>
+int launch_stream4_mode(FusedArgs& A, cudaStream_t stream) {
+    if (!getenv("MXADV_NO_TMA") && stream4_tmap<PPM>(A)) return launch_stream4_tma<PPM, true>(A, stream);
+    return launch_stream4_tma<PPM, false>(A, stream);
 }
 
 #endif

@@ -1,2 +1,1 @@
-scripts/gpu.sh k6first 2>&1 | grep -v "^$" | tail -12
-TAG=k6 scripts/gpu.sh prof 256 k_stream6
+TAG=tma1 scripts/gpu.sh first 2>&1 | grep -v "^$" | tail -14

@@ -24,18 +24,15 @@ except Exception as e:
 PY
 }
 case $task in
-  k6first)   # first contact of a new kernel: parity of the new kernel, then A/B timing
-    # a hung kernel must not eat the lease: one tiny launch with a short leash first
+  first)     # first contact of a changed kernel: smoke on a short leash, TMA parity, then A/B timing
     if ! timeout -k 5 150 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; then
       echo "SMOKE FAILED OR HUNG (rc $?)"; tail -5 $out/smoke.log; exit 1
     fi
     tail -2 $out/smoke.log
-    timeout -k 10 900 python -m pytest tests/test_gpu_stream6.py -x -q -m gpu 2>&1 | tail -15 | tee $out/pytest_stream6.log
-    bench 256_v4 MXADV_KERNEL=v4 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
-    bench 256_k6 X=1 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
-    bench 256_fmad_k6 MXADV_LIB=exp/fmad/libmxadv.so -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
-    bench 256_fmad_v4 MXADV_LIB=exp/fmad/libmxadv.so MXADV_KERNEL=v4 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
-    bench 512_k6 X=1 -- --size 512 --steps 5 --warmup 3 --no-cpu --no-e2e
+    timeout -k 10 900 python -m pytest tests/test_gpu_tma.py -x -q -m gpu 2>&1 | tail -15 | tee $out/pytest_tma.log
+    bench 256_tma X=1 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
+    bench 256_cpasync MXADV_NO_TMA=1 -- --size 256 --steps 5 --warmup 3 --no-cpu --no-e2e
+    bench 512_tma X=1 -- --size 512 --steps 5 --warmup 3 --no-cpu --no-e2e
     ;;
   tests)     # the whole GPU suite
     timeout -k 10 ${T:-2400} python -m pytest tests -x -q -m gpu "$@" 2>&1 | tail -25 | tee $out/pytest_gpu.log
@@ -53,5 +50,5 @@ case $task in
       -o $out/prof_${tag} -f python bench.py --size $size --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_${tag}.log 2>&1
     tail -3 $out/ncu_${tag}.log
     ;;
-  *) echo "tasks: k6first | tests | ab <size> <names...>"; exit 2;;
+  *) echo "tasks: first | tests | ab <size> <names...> | prof <size> <regex>"; exit 2;;
 esac

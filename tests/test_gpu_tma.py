@@ -1,9 +1,11 @@
-"""k_stream6 (role-specialised, TMA-fed streaming kernel) and k_stream4 (cp.async kernel) against
-the oracle on the same inputs, bit for bit, with a check of WHICH kernel ran.
+"""k_stream4 with its shared-memory ring filled by TMA (cp.async.bulk.tensor + mbarrier) and
+with the cp.async fallback, against the oracle on the same inputs, bit for bit, with a check of
+WHICH staging ran.
 
 TMA needs fab rows of an even number of doubles and a 16-byte aligned base; boxes that do not
-qualify take k_stream4.  Every case here has even rows, so the default dispatch must launch
-k_stream6 (mx_tma_launch_count() > 0) and MXADV_KERNEL=v4 must not."""
+qualify take the cp.async instantiation.  Every case here has even rows, so the default
+dispatch must launch the TMA instantiation (mx_tma_launch_count() > 0) and MXADV_NO_TMA=1 must
+not.  (tests/test_gpu_parity.py holds the odd-row boxes.)"""
 import numpy as np
 import pytest
 
@@ -25,13 +27,13 @@ def mxl():
 def _expect_kernel(lib, kernel):
     n_all, n_tma = lib.mx_launch_count(), lib.mx_tma_launch_count()
     assert n_all > 0
-    if kernel == "v4":
-        assert n_tma == 0, "MXADV_KERNEL=v4 still launched the TMA kernel"
+    if kernel == "cp.async":
+        assert n_tma == 0, "MXADV_NO_TMA=1 still launched the TMA instantiation"
     else:
-        assert n_tma > 0, "even-row box did not take the TMA kernel"
+        assert n_tma > 0, "even-row box did not take the TMA instantiation"
 
 
-KERNELS = [None, "v4"]
+KERNELS = [None, "cp.async"]
 # (ppm, slope_order, bc kind, is_vel)
 EDGE_CASES = [
     (0, 4, "periodic", 0), (0, 2, "mixed", 0), (0, 4, "outflow", 0), (0, 0, "periodic", 0),
@@ -50,7 +52,7 @@ def test_edge_states(mxl, oracle_calls, case, n, zchunk, kernel, monkeypatch):
     lib, mx = mxl
     ppm, so, bck, is_vel = case
     if kernel:
-        monkeypatch.setenv("MXADV_KERNEL", kernel)
+        monkeypatch.setenv("MXADV_NO_TMA", "1")
     if zchunk:
         monkeypatch.setenv("MXADV_ZCHUNK", zchunk)
     ng = 4 if ppm == 2 else 3
@@ -84,7 +86,7 @@ def test_density_pass(mxl, oracle_calls, ppm, bck, spt, nspec, n, sph, kernel, m
     from maestroex_b200.fusedcalls import density_edge_flux
     lib, mx = mxl
     if kernel:
-        monkeypatch.setenv("MXADV_KERNEL", kernel)
+        monkeypatch.setenv("MXADV_NO_TMA", "1")
     ng = 4 if ppm == 2 else 3
     prob = make_problem(dim=3, n=n, nspec=nspec, ng=ng, bc_kind=bck, seed=62, spherical=sph)
     epar = prob.edge_params(FIRSTSPEC, nspec, ppm_type=ppm)
@@ -109,7 +111,7 @@ def test_enthalpy_pass(mxl, oracle_calls, ppm, ept, spt, kernel, monkeypatch):
     from maestroex_b200.fusedcalls import enthalpy_edge_flux
     lib, mx = mxl
     if kernel:
-        monkeypatch.setenv("MXADV_KERNEL", kernel)
+        monkeypatch.setenv("MXADV_NO_TMA", "1")
     ng = 4 if ppm == 2 else 3
     prob = make_problem(dim=3, n=(34, 30, 26), nspec=3, ng=ng, bc_kind="reacting_bubble", seed=63)
     # sedge(Rho) from an earlier density pass is an input of the h-type flux forms
@@ -137,7 +139,7 @@ def test_enthalpy_pass(mxl, oracle_calls, ppm, ept, spt, kernel, monkeypatch):
                                               (1, 2, 3, 0), (1, 1, 1, 1)])
 def test_enthalpy_pass_spherical(mxl, oracle_calls, ppm, ept, spt, exact, residency):
     """mx_enthalpy_edge_flux_sph == MakeEdgeScal(RhoH) + MakeRhoHFlux with the spherical flux
-    forms (MaestroMakeFlux.cpp:788-1021): fused in k_stream6 unless use_exact_base_state."""
+    forms (MaestroMakeFlux.cpp:788-1021): fused in k_stream4 unless use_exact_base_state."""
     import torch
     from gpu_util import to_device, to_host
     from maestroex_b200.abi import Fab
