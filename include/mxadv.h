@@ -353,6 +353,97 @@ int mx_halo_exchange(MxComm* comm, const MxGeom* geom, const MxFab* fab, int ng,
 /* bytes this rank sent during its last mx_halo_exchange */
 long long mx_comm_bytes_sent(const MxComm* comm);
 
+
+/* ==== the passes either side of the path ==================
+ * One box of one level each, like everything above; ghost fills (FillPatch), AverageDown and
+ * the AMR tails of the reference members stay with the caller.  Fabs and 1-D arrays may be
+ * host or device resident. */
+
+/* Maestro::ConvertRhoXToX / ConvertRhoHToH (Source/MaestroConvert.cpp:64-114): components
+ * [start_comp, start_comp+num_comp) of `scal` divided (flag != 0) or multiplied (flag == 0) by
+ * component rho_comp on the valid box (MultiFab::Divide / Multiply with 0 ghost cells). */
+int mx_convert_by_rho(const MxGeom* geom, const MxFab* scal, int rho_comp, int start_comp,
+                      int num_comp, int flag, void* stream);
+
+/* What the 1-D -> 3-D mappings of Source/MaestroFill3dData.cpp read besides their arguments:
+ * base_geom (Source/BaseStateGeometry.H: nr_fine, dr_fine, r_cc_loc, r_edge_loc at level 0),
+ * the Maestro members `center` and geom[lev].ProbLo, and the maestro.*_interp_type runtime
+ * parameters (Source/param/_cpp_parameters:527-546).  Only read when `spherical`. */
+typedef struct MxSphr {
+    int spherical;
+    int nr_fine;
+    double dr_fine;
+    double prob_lo[3];
+    double center[3];
+    const double* r_cc_loc;   /* nr_fine */
+    const double* r_edge_loc; /* nr_fine + 1 */
+    int s0_interp_type, w0_interp_type, s0mac_interp_type, w0mac_interp_type;
+} MxSphr;
+
+/* Maestro::Put1dArrayOnCart, per-level body (Source/MaestroFill3dData.cpp:48-337) on the valid
+ * box of s0_cart: planar s0_cart(i,j,k,outcomp) = s0(lev,r) or 0.5 (s0(lev,r) + s0(lev,r+1))
+ * with r the last index (outcomp = dim-1 if is_output_a_vector else 0); spherical (3-D,
+ * !use_exact_base_state) the piecewise-constant / linear / quadratic interpolations in radius
+ * selected by w0_interp_type (edge-centred input) or s0_interp_type (cell-centred input), times
+ * the unit normal if is_output_a_vector (3 components). */
+int mx_put_1d_array_on_cart(const MxGeom* geom, const MxBase* s0, int lev, const MxFab* s0_cart,
+                            int is_input_edge_centered, int is_output_a_vector,
+                            const MxSphr* sphr, void* stream);
+
+/* Maestro::PutInPertForm (Source/MaestroConvert.cpp:6-62) without the s0_cart temporary:
+ * scal(comp) -= s0 mapped onto the box (flag != 0) or += (flag == 0), valid box only; the
+ * mapping is Put1dArrayOnCart(s0, ., false, false). */
+int mx_put_in_pert_form(const MxGeom* geom, const MxFab* scal, const MxBase* s0, int lev, int comp,
+                        int flag, const MxSphr* sphr, void* stream);
+
+/* Maestro::ModifyScalForce (Source/MaestroForce.cpp:261-467), zone loop on the valid box:
+ * scal_force(comp) -= scal div(U)                         (fullform == 1)
+ * scal_force(comp) += -(scal - s0) div(U) - div(s0 U)     (fullform == 0)
+ * umac does NOT contain w0 here.  Planar: s0_cart (1 comp, >= 0 ghosts: only the zone itself is
+ * read), w0_cart (the Maestro member, dim comps, 1 ghost) and the 1-D s0_edge, which the
+ * reference maps onto a 1-ghost MultiFab with Put1dArrayOnCart(s0_edge, ., false, false, bcs_f):
+ * the face above the box's top zone is s0_edge(r+1) inside the domain and the bcs_f fill of it
+ * at the top domain face (bcf_hi: MX_BC_FOEXTRAP / MX_BC_REFLECT_EVEN -> s0_edge(domhi),
+ * MX_BC_INT_DIR (periodic) -> s0_edge(domlo)).  Spherical (3-D): s0_cart with 1 ghost,
+ * div(w0) evaluated from the 1-D w0 (nr_fine+1) as the reference does (divw0 table, then
+ * Put1dArrayOnCart(divw0, ., false, false)); w0_cart and s0_edge are not read. */
+int mx_modify_scal_force(const MxGeom* geom, const MxFab* scal_force, const MxFab* state,
+                         const MxFab* umac /*[dim]*/, const MxBase* s0_edge, int lev,
+                         const MxFab* s0_cart, const MxFab* w0_cart, const double* w0,
+                         int comp, int fullform, int bcf_hi, const MxSphr* sphr, void* stream);
+
+/* Maestro::Addw0 (Source/MaestroFill3dData.cpp:357-461), the add itself: planar
+ * uedge[dim-1](i,j,r) += mult * w0(lev,r) on the nodal valid box grown by one in the transverse
+ * directions; spherical uedge[d] += mult * w0mac[d] on the nodal valid boxes.  The ghost fill
+ * that follows (FillBoundary / FillUmacGhost) is the caller's. */
+int mx_addw0(const MxGeom* geom, const MxFab* uedge /*[dim]*/, const MxFab* w0mac /*[3] or NULL*/,
+             const MxBase* w0, int lev, double mult, int spherical, void* stream);
+
+/* Maestro::MakeW0mac (Source/MaestroFill3dData.cpp:464-710; spherical, 3-D): w0mac[d] on the
+ * nodal valid box grown by one (w0mac has 1 ghost cell), from w0_cart (w0mac_interp_type 1:
+ * the Maestro member, 3 comps, >= 2 ghost cells... the average reads one cell beyond the grown
+ * face box) or from the 1-D w0 directly (types 2, 3; type 4 through nodal values). */
+int mx_make_w0mac(const MxGeom* geom, const MxFab* w0mac /*[3]*/, const MxFab* w0_cart,
+                  const double* w0, const MxSphr* sphr, void* stream);
+
+/* Maestro::MakeS0mac (Source/MaestroFill3dData.cpp:712-1188; spherical, 3-D,
+ * !use_exact_base_state): s0mac[d] on the nodal valid box grown by one.  s0mac_interp_type 1
+ * averages the cell-centred mapping of s0 (Put1dArrayOnCart + FillPatch with bcs_f in the
+ * reference: cells outside the domain take the first-order extrapolation, i.e. the value of the
+ * nearest cell inside; evaluated on the fly here, no s0_cart temporary); types 2 and 3
+ * interpolate to the face centres directly. */
+int mx_make_s0mac(const MxGeom* geom, const MxBase* s0, const MxFab* s0mac /*[3]*/,
+                  const MxSphr* sphr, void* stream);
+
+/* Maestro::UpdateVel (Source/MaestroAdvection.cpp:299-526), zone loop on the valid box:
+ * unew = uold - dt (Utilde . grad) Utilde + dt force - dt (w0 . grad) Utilde, times the sponge.
+ * umac, uedge[d] (dim comps, face centred), force (dim comps), sponge (1 comp, read if
+ * do_sponge), w0_cart (planar; dim comps, 1 ghost in the last direction) or w0mac (spherical). */
+int mx_update_vel(const MxGeom* geom, const MxFab* uold, const MxFab* unew, const MxFab* umac,
+                  const MxFab* uedge, const MxFab* force, const MxFab* sponge,
+                  const MxFab* w0_cart, const MxFab* w0mac, double dt, int do_sponge,
+                  int spherical, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

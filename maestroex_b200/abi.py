@@ -309,5 +309,51 @@ class UpdateParams:
         return p
 
 
+class MxSphr(C.Structure):
+    _fields_ = [
+        ("spherical", C.c_int),
+        ("nr_fine", C.c_int),
+        ("dr_fine", C.c_double),
+        ("prob_lo", C.c_double * 3),
+        ("center", C.c_double * 3),
+        ("r_cc_loc", C.c_void_p),
+        ("r_edge_loc", C.c_void_p),
+        ("s0_interp_type", C.c_int),
+        ("w0_interp_type", C.c_int),
+        ("s0mac_interp_type", C.c_int),
+        ("w0mac_interp_type", C.c_int),
+    ]
+
+
+@dataclass
+class Sphr:
+    """base_geom / center / interp types read by the 1-D -> 3-D mappings
+    (Source/MaestroFill3dData.cpp); r_cc_loc / r_edge_loc are HOST numpy arrays."""
+    nr_fine: int
+    dr_fine: float
+    prob_lo: tuple
+    center: tuple
+    r_cc_loc: object
+    r_edge_loc: object
+    s0_interp_type: int = 3
+    w0_interp_type: int = 2
+    s0mac_interp_type: int = 1
+    w0mac_interp_type: int = 1
+    spherical: int = 1
+
+    def c(self) -> MxSphr:
+        p = MxSphr()
+        p.spherical = self.spherical
+        p.nr_fine = self.nr_fine
+        p.dr_fine = self.dr_fine
+        p.prob_lo[:] = self.prob_lo
+        p.center[:] = self.center
+        p.r_cc_loc = _ptr_of(self.r_cc_loc)
+        p.r_edge_loc = _ptr_of(self.r_edge_loc)
+        for n in ("s0_interp_type", "w0_interp_type", "s0mac_interp_type", "w0mac_interp_type"):
+            setattr(p, n, int(getattr(self, n)))
+        return p
+
+
 def byref_or_null(x):
     return C.byref(x) if x is not None else None

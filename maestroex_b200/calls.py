@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-from .abi import Base, EdgeParams, Fab, FluxParams, Geom, fab_array  # noqa: F401
+from .abi import Base, EdgeParams, Fab, FluxParams, Geom, Sphr, fab_array  # noqa: F401
 
 
 class MxError(RuntimeError):
@@ -147,3 +147,80 @@ class Calls:
                                      *self._tail(stream))
         self._check(rc, "update_scal")
         return n.value
+
+    # ==== the passes either side of the path ==============
+    @staticmethod
+    def _sphr(s):
+        return C.byref(s.c()) if s is not None else None
+
+    @staticmethod
+    def _fab(f):
+        return C.byref(f.c()) if f is not None else None
+
+    # -- Maestro::ConvertRhoXToX / ConvertRhoHToH (Source/MaestroConvert.cpp:64-114) ------
+    def convert_by_rho(self, geom: Geom, scal: Fab, rho_comp: int, start_comp: int, num_comp: int,
+                       flag: bool, stream: int = 0):
+        g, s = geom.c(), scal.c()
+        rc = self._fn("convert_by_rho")(C.byref(g), C.byref(s), rho_comp, start_comp, num_comp,
+                                        int(bool(flag)), *self._tail(stream))
+        self._check(rc, "convert_by_rho")
+
+    # -- Maestro::Put1dArrayOnCart (Source/MaestroFill3dData.cpp:48-337) ------------------
+    def put_1d_array_on_cart(self, geom: Geom, s0: Base, lev: int, s0_cart: Fab, edge: bool,
+                             vec: bool, sphr: Sphr = None, stream: int = 0):
+        g, f = geom.c(), s0_cart.c()
+        rc = self._fn("put_1d_array_on_cart")(C.byref(g), self._base(s0), lev, C.byref(f),
+                                              int(bool(edge)), int(bool(vec)), self._sphr(sphr),
+                                              *self._tail(stream))
+        self._check(rc, "put_1d_array_on_cart")
+
+    # -- Maestro::PutInPertForm (Source/MaestroConvert.cpp:6-62) --------------------------
+    def put_in_pert_form(self, geom: Geom, scal: Fab, s0: Base, lev: int, comp: int, flag: bool,
+                         sphr: Sphr = None, stream: int = 0):
+        g, f = geom.c(), scal.c()
+        rc = self._fn("put_in_pert_form")(C.byref(g), C.byref(f), self._base(s0), lev, comp,
+                                          int(bool(flag)), self._sphr(sphr), *self._tail(stream))
+        self._check(rc, "put_in_pert_form")
+
+    # -- Maestro::ModifyScalForce (Source/MaestroForce.cpp:261-467) -----------------------
+    def modify_scal_force(self, geom: Geom, scal_force: Fab, state: Fab, umac, s0_edge: Base,
+                          lev: int, s0_cart: Fab, w0_cart: Fab, w0, comp: int, fullform: int,
+                          bcf_hi: int, sphr: Sphr = None, stream: int = 0):
+        g, f, st, s0c = geom.c(), scal_force.c(), state.c(), s0_cart.c()
+        rc = self._fn("modify_scal_force")(
+            C.byref(g), C.byref(f), C.byref(st), self._faces(umac), self._base(s0_edge), lev,
+            C.byref(s0c), self._fab(w0_cart), self._vp(w0), comp, fullform, bcf_hi,
+            self._sphr(sphr), *self._tail(stream))
+        self._check(rc, "modify_scal_force")
+
+    # -- Maestro::Addw0 (Source/MaestroFill3dData.cpp:357-461) ----------------------------
+    def addw0(self, geom: Geom, uedge, w0mac, w0: Base, lev: int, mult: float, spherical: int,
+              stream: int = 0):
+        g = geom.c()
+        rc = self._fn("addw0")(C.byref(g), self._faces(uedge), self._faces(w0mac), self._base(w0),
+                               lev, C.c_double(mult), spherical, *self._tail(stream))
+        self._check(rc, "addw0")
+
+    # -- Maestro::MakeW0mac / MakeS0mac (Source/MaestroFill3dData.cpp:464-1188) -----------
+    def make_w0mac(self, geom: Geom, w0mac, w0_cart: Fab, w0, sphr: Sphr, stream: int = 0):
+        g = geom.c()
+        rc = self._fn("make_w0mac")(C.byref(g), self._faces(w0mac), self._fab(w0_cart),
+                                    self._vp(w0), self._sphr(sphr), *self._tail(stream))
+        self._check(rc, "make_w0mac")
+
+    def make_s0mac(self, geom: Geom, s0: Base, s0mac, sphr: Sphr, stream: int = 0):
+        g = geom.c()
+        rc = self._fn("make_s0mac")(C.byref(g), self._base(s0), self._faces(s0mac),
+                                    self._sphr(sphr), *self._tail(stream))
+        self._check(rc, "make_s0mac")
+
+    # -- Maestro::UpdateVel (Source/MaestroAdvection.cpp:299-526) -------------------------
+    def update_vel(self, geom: Geom, uold: Fab, unew: Fab, umac, uedge, force: Fab, sponge: Fab,
+                   w0_cart: Fab, w0mac, dt: float, do_sponge: int, spherical: int,
+                   stream: int = 0):
+        g, uo, un, fo = geom.c(), uold.c(), unew.c(), force.c()
+        rc = self._fn("update_vel")(C.byref(g), C.byref(uo), C.byref(un), self._faces(umac),
+                                    self._faces(uedge), C.byref(fo), self._fab(sponge),
+                                    self._fab(w0_cart), self._faces(w0mac), C.c_double(dt),
+                                    do_sponge, spherical, *self._tail(stream))
+        self._check(rc, "update_vel")

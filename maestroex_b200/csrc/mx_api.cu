@@ -17,6 +17,7 @@
 #include "mx_flux.h"
 #include "mx_w0.h"
 #include "mx_update.h"
+#include "mx_cart.h"
 #include "mx_fused.h"
 #include "mx_staged.h"
 
@@ -1196,6 +1197,323 @@ int mx_halo_unpack(const MxGeom* geom, const MxFab* fab, int dir, int side, int 
                    int ncomp, const double* buf, void* stream) {
     return halo_common(geom, fab, dir, side, ng, comp0, ncomp, const_cast<double*>(buf), true,
                        stream);
+}
+
+}  // extern "C"
+
+// ==== the passes either side of the path (mx_cart.cu) ======================================
+namespace {
+// device copy of the MxSphr tables
+int make_ksphr(Session& S, const MxSphr* sp, KSphr* out) {
+    memset(out, 0, sizeof(*out));
+    if (sp == nullptr || !sp->spherical) return MX_OK;
+    if (sp->nr_fine < 3 || !sp->r_cc_loc || !sp->r_edge_loc || !(sp->dr_fine > 0.0))
+        return fail(MX_ERR_INVALID, "MxSphr: nr_fine / dr_fine / r_cc_loc / r_edge_loc");
+    out->spherical = 1;
+    out->nr = sp->nr_fine;
+    out->drf = sp->dr_fine;
+    for (int d = 0; d < 3; ++d) {
+        out->plo[d] = sp->prob_lo[d];
+        out->cen[d] = sp->center[d];
+    }
+    out->s0t = sp->s0_interp_type;
+    out->w0t = sp->w0_interp_type;
+    out->s0mt = sp->s0mac_interp_type;
+    out->w0mt = sp->w0mac_interp_type;
+    const MxBase cc = {sp->r_cc_loc, 1, sp->nr_fine, 1}, ec = {sp->r_edge_loc, 1, sp->nr_fine + 1, 1};
+    int st;
+    MX_TRY(S.base(&cc, 0, &out->rcc, &st));
+    MX_TRY(S.base(&ec, 0, &out->redge, &st));
+    return MX_OK;
+}
+int check_type(int t, int hi, const char* name) {
+    if (t < 1 || t > hi) return fail(MX_ERR_INVALID, "%s = %d out of range 1..%d", name, t, hi);
+    return MX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mx_convert_by_rho(const MxGeom* geom, const MxFab* scal, int rho_comp, int start_comp,
+                      int num_comp, int flag, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!scal) return fail(MX_ERR_INVALID, "null argument");
+    if (rho_comp < 0 || rho_comp >= scal->ncomp || start_comp < 0 || num_comp < 0 ||
+        start_comp + num_comp > scal->ncomp || (rho_comp >= start_comp && rho_comp < start_comp + num_comp))
+        return fail(MX_ERR_INVALID, "bad component range");
+    MX_TRY(check_cover(geom, scal, 0, -1, "scal"));
+    MX_TRY(require_device());
+    Session S(stream);
+    DFab d;
+    MX_TRY(S.fab(scal, &d, start_comp, num_comp, true, true));
+    MX_TRY(S.upload(scal, d, rho_comp, 1));
+    cart_convert_by_rho(make_kgeom(geom), d, rho_comp, start_comp, num_comp, flag, S.stream());
+    return S.finish();
+}
+
+int mx_put_1d_array_on_cart(const MxGeom* geom, const MxBase* s0, int lev, const MxFab* s0_cart,
+                            int is_input_edge_centered, int is_output_a_vector,
+                            const MxSphr* sphr, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!s0 || !s0->p || !s0_cart) return fail(MX_ERR_INVALID, "null argument");
+    const bool sph = sphr && sphr->spherical;
+    if (sph && geom->dim != 3) return fail(MX_ERR_INVALID, "Spherical is not valid for DIM < 3");
+    if (s0_cart->ncomp < (is_output_a_vector ? geom->dim : 1))
+        return fail(MX_ERR_INVALID, "s0_cart has too few components");
+    if (sph) {
+        MX_TRY(check_type(is_input_edge_centered ? sphr->w0_interp_type : sphr->s0_interp_type, 3,
+                          is_input_edge_centered ? "w0_interp_type" : "s0_interp_type"));
+    } else {
+        const int last = geom->dim - 1;
+        if (geom->valid_lo[last] < 0 || geom->valid_hi[last] + (is_input_edge_centered ? 1 : 0) >= s0->len)
+            return fail(MX_ERR_INVALID, "s0 does not cover the box");
+    }
+    MX_TRY(check_cover(geom, s0_cart, 0, -1, "s0_cart"));
+    MX_TRY(require_device());
+    Session S(stream);
+    KSphr ks;
+    MX_TRY(make_ksphr(S, sphr, &ks));
+    const double* p;
+    int st;
+    MX_TRY(S.base(s0, sph ? 0 : lev, &p, &st));
+    DFab d;
+    const int oc = sph ? 0 : (is_output_a_vector ? geom->dim - 1 : 0);
+    const int nc = (sph && is_output_a_vector) ? 3 : 1;
+    // valid zones only are written: a host mirror starts from the caller's data
+    MX_TRY(S.fab(s0_cart, &d, oc, nc, true, true));
+    cart_put_1d(make_kgeom(geom), p, st, d, is_input_edge_centered, is_output_a_vector, 0, 0, ks, S.stream());
+    return S.finish();
+}
+
+int mx_put_in_pert_form(const MxGeom* geom, const MxFab* scal, const MxBase* s0, int lev, int comp,
+                        int flag, const MxSphr* sphr, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!s0 || !s0->p || !scal) return fail(MX_ERR_INVALID, "null argument");
+    const bool sph = sphr && sphr->spherical;
+    if (sph && geom->dim != 3) return fail(MX_ERR_INVALID, "Spherical is not valid for DIM < 3");
+    if (comp < 0 || comp >= scal->ncomp) return fail(MX_ERR_INVALID, "bad component");
+    if (sph) {
+        MX_TRY(check_type(sphr->s0_interp_type, 3, "s0_interp_type"));
+    } else {
+        const int last = geom->dim - 1;
+        if (geom->valid_lo[last] < 0 || geom->valid_hi[last] >= s0->len)
+            return fail(MX_ERR_INVALID, "s0 does not cover the box");
+    }
+    MX_TRY(check_cover(geom, scal, 0, -1, "scal"));
+    MX_TRY(require_device());
+    Session S(stream);
+    KSphr ks;
+    MX_TRY(make_ksphr(S, sphr, &ks));
+    const double* p;
+    int st;
+    MX_TRY(S.base(s0, sph ? 0 : lev, &p, &st));
+    DFab d;
+    MX_TRY(S.fab(scal, &d, comp, 1, true, true));
+    cart_put_1d(make_kgeom(geom), p, st, d, 0, 0, flag ? 1 : 2, comp, ks, S.stream());
+    return S.finish();
+}
+
+int mx_modify_scal_force(const MxGeom* geom, const MxFab* scal_force, const MxFab* state,
+                         const MxFab* umac, const MxBase* s0_edge, int lev, const MxFab* s0_cart,
+                         const MxFab* w0_cart, const double* w0, int comp, int fullform, int bcf_hi,
+                         const MxSphr* sphr, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!scal_force || !state || !umac || !s0_cart) return fail(MX_ERR_INVALID, "null argument");
+    const bool sph = sphr && sphr->spherical;
+    if (sph && geom->dim != 3) return fail(MX_ERR_INVALID, "ModifyScalForce: Spherical is not valid for DIM < 3");
+    if (comp < 0 || comp >= state->ncomp || comp >= scal_force->ncomp)
+        return fail(MX_ERR_INVALID, "bad component");
+    if (sph) {
+        if (!w0) return fail(MX_ERR_INVALID, "spherical: w0 is required");
+        MX_TRY(check_type(sphr->s0_interp_type, 3, "s0_interp_type"));
+        MX_TRY(check_cover(geom, s0_cart, fullform == 1 ? 0 : 1, -1, "s0_cart"));
+    } else {
+        if (!w0_cart || !s0_edge || !s0_edge->p) return fail(MX_ERR_INVALID, "planar: w0_cart and s0_edge are required");
+        if (w0_cart->ncomp < geom->dim) return fail(MX_ERR_INVALID, "w0_cart needs dim components");
+        if (bcf_hi != MX_BC_INT_DIR && bcf_hi != MX_BC_FOEXTRAP && bcf_hi != MX_BC_REFLECT_EVEN)
+            return fail(MX_ERR_INVALID, "bcf_hi must be a bcs_f code (int_dir, foextrap, reflect_even)");
+        const int last = geom->dim - 1;
+        if (geom->valid_lo[last] < 0 || geom->valid_hi[last] + 1 >= s0_edge->len)
+            return fail(MX_ERR_INVALID, "s0_edge does not cover the box");
+        MX_TRY(check_cover(geom, s0_cart, 0, -1, "s0_cart"));
+        for (int d = 0; d < geom->dim; ++d) {  // one ghost cell above in the last direction
+            const int ng = d == last ? 1 : 0;
+            if (w0_cart->lo[d] > geom->valid_lo[d] || w0_cart->hi[d] < geom->valid_hi[d] + ng)
+                return fail(MX_ERR_INVALID, "w0_cart needs one ghost cell in the last direction");
+        }
+    }
+    MX_TRY(check_cover(geom, scal_force, 0, -1, "scal_force"));
+    MX_TRY(check_cover(geom, state, 0, -1, "state"));
+    MX_TRY(require_device());
+    Session S(stream);
+    KSphr ks;
+    MX_TRY(make_ksphr(S, sphr, &ks));
+    DFab f, stt, um[3], s0c, w0c;
+    memset(&w0c, 0, sizeof(w0c));
+    MX_TRY(S.fab(scal_force, &f, comp, 1, true, true));
+    MX_TRY(S.fab(state, &stt, comp, 1, true, false));
+    for (int d = 0; d < geom->dim; ++d) {
+        MX_TRY(check_cover(geom, &umac[d], 0, d, "umac"));
+        MX_TRY(S.fab(&umac[d], &um[d], 0, 1, true, false));
+    }
+    MX_TRY(S.fab(s0_cart, &s0c, 0, 1, true, false));
+    const double* pe = nullptr;
+    int ste = 1;
+    const double* dw0 = nullptr;
+    double* ws = nullptr;
+    if (sph) {
+        const MxBase bw = {w0, 1, sphr->nr_fine + 1, 1};
+        int st;
+        MX_TRY(S.base(&bw, 0, &dw0, &st));
+        void* q = nullptr;
+        CUDA_OK(S.alloc(&q, sizeof(double) * (size_t)sphr->nr_fine));
+        ws = static_cast<double*>(q);
+    } else {
+        MX_TRY(S.fab(w0_cart, &w0c, geom->dim - 1, 1, true, false));
+        MX_TRY(S.base(s0_edge, lev, &pe, &ste));
+    }
+    cart_modify_scal_force(make_kgeom(geom), f, stt, um, pe, ste, s0c, w0c, dw0, ws, comp, fullform, bcf_hi,
+                           ks, S.stream());
+    return S.finish();
+}
+
+int mx_addw0(const MxGeom* geom, const MxFab* uedge, const MxFab* w0mac, const MxBase* w0, int lev,
+             double mult, int spherical, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!uedge) return fail(MX_ERR_INVALID, "null argument");
+    if (spherical && geom->dim != 3) return fail(MX_ERR_INVALID, "Addw0: Spherical is not valid for DIM < 3");
+    if (spherical && !w0mac) return fail(MX_ERR_INVALID, "spherical: w0mac is required");
+    if (!spherical && (!w0 || !w0->p)) return fail(MX_ERR_INVALID, "planar: w0 is required");
+    MX_TRY(require_device());
+    Session S(stream);
+    const KGeom kg = make_kgeom(geom);
+    DFab ue[3], wm[3];
+    const double* pw = nullptr;
+    int stw = 1;
+    if (spherical) {
+        for (int d = 0; d < 3; ++d) {
+            MX_TRY(check_cover(geom, &uedge[d], 0, d, "uedge"));
+            MX_TRY(check_cover(geom, &w0mac[d], 0, d, "w0mac"));
+            MX_TRY(S.fab(&uedge[d], &ue[d], 0, 1, true, true));
+            MX_TRY(S.fab(&w0mac[d], &wm[d], 0, 1, true, false));
+        }
+    } else {
+        const int last = geom->dim - 1;
+        if (geom->valid_lo[last] < 0 || geom->valid_hi[last] + 1 >= w0->len)
+            return fail(MX_ERR_INVALID, "w0 does not cover the box");
+        for (int d = 0; d < geom->dim; ++d) {  // one ghost cell in the transverse directions
+            const int ng = d == last ? 0 : 1;
+            const int hi = geom->valid_hi[d] + (d == last ? 1 : 0);
+            if (uedge[last].lo[d] > geom->valid_lo[d] - ng || uedge[last].hi[d] < hi + ng)
+                return fail(MX_ERR_INVALID, "uedge needs one transverse ghost cell");
+        }
+        MX_TRY(S.fab(&uedge[last], &ue[last], 0, 1, true, true));
+        MX_TRY(S.base(w0, lev, &pw, &stw));
+    }
+    cart_addw0(kg, ue, wm, pw, stw, mult, spherical, S.stream());
+    return S.finish();
+}
+
+int mx_make_w0mac(const MxGeom* geom, const MxFab* w0mac, const MxFab* w0_cart, const double* w0,
+                  const MxSphr* sphr, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!w0mac || !sphr) return fail(MX_ERR_INVALID, "null argument");
+    if (!sphr->spherical || geom->dim != 3) return fail(MX_ERR_INVALID, "Error: only call MakeW0mac for spherical");
+    MX_TRY(check_type(sphr->w0mac_interp_type, 4, "w0mac_interp_type"));
+    const int type = sphr->w0mac_interp_type;
+    if (type == 1 && !w0_cart) return fail(MX_ERR_INVALID, "w0mac_interp_type 1: w0_cart is required");
+    if (type != 1 && !w0) return fail(MX_ERR_INVALID, "w0 is required");
+    for (int d = 0; d < 3; ++d) MX_TRY(check_cover(geom, &w0mac[d], 1, d, "w0mac"));
+    if (type == 1) MX_TRY(check_cover(geom, w0_cart, 2, -1, "w0_cart"));
+    MX_TRY(require_device());
+    Session S(stream);
+    KSphr ks;
+    MX_TRY(make_ksphr(S, sphr, &ks));
+    DFab wm[3], w0c;
+    memset(&w0c, 0, sizeof(w0c));
+    for (int d = 0; d < 3; ++d) MX_TRY(S.fab(&w0mac[d], &wm[d], 0, 1, true, true));
+    const double* dw0 = nullptr;
+    if (type == 1) {
+        MX_TRY(S.fab(w0_cart, &w0c, 0, 3, true, false));
+    } else {
+        const MxBase bw = {w0, 1, sphr->nr_fine + 1, 1};
+        int st;
+        MX_TRY(S.base(&bw, 0, &dw0, &st));
+    }
+    cart_make_w0mac(make_kgeom(geom), wm, w0c, dw0, ks, S.stream());
+    return S.finish();
+}
+
+int mx_make_s0mac(const MxGeom* geom, const MxBase* s0, const MxFab* s0mac, const MxSphr* sphr,
+                  void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!s0mac || !sphr || !s0 || !s0->p) return fail(MX_ERR_INVALID, "null argument");
+    if (!sphr->spherical || geom->dim != 3) return fail(MX_ERR_INVALID, "Error: only call MakeS0mac for spherical");
+    MX_TRY(check_type(sphr->s0mac_interp_type, 3, "s0mac_interp_type"));
+    if (sphr->s0mac_interp_type == 1) MX_TRY(check_type(sphr->s0_interp_type, 3, "s0_interp_type"));
+    for (int d = 0; d < 3; ++d) MX_TRY(check_cover(geom, &s0mac[d], 1, d, "s0mac"));
+    MX_TRY(require_device());
+    Session S(stream);
+    KSphr ks;
+    MX_TRY(make_ksphr(S, sphr, &ks));
+    DFab sm[3];
+    for (int d = 0; d < 3; ++d) MX_TRY(S.fab(&s0mac[d], &sm[d], 0, 1, true, true));
+    const double* p;
+    int st;
+    MX_TRY(S.base(s0, 0, &p, &st));
+    cart_make_s0mac(make_kgeom(geom), p, st, sm, ks, S.stream());
+    return S.finish();
+}
+
+int mx_update_vel(const MxGeom* geom, const MxFab* uold, const MxFab* unew, const MxFab* umac,
+                  const MxFab* uedge, const MxFab* force, const MxFab* sponge, const MxFab* w0_cart,
+                  const MxFab* w0mac, double dt, int do_sponge, int spherical, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!uold || !unew || !umac || !uedge || !force) return fail(MX_ERR_INVALID, "null argument");
+    if (spherical && geom->dim != 3) return fail(MX_ERR_INVALID, "UpdateVel: Spherical is not valid for DIM < 3");
+    if (spherical ? !w0mac : !w0_cart) return fail(MX_ERR_INVALID, "w0_cart (planar) / w0mac (spherical) is required");
+    if (do_sponge && !sponge) return fail(MX_ERR_INVALID, "do_sponge: sponge is required");
+    const int dim = geom->dim;
+    if (uold->ncomp < dim || unew->ncomp < dim || force->ncomp < dim)
+        return fail(MX_ERR_INVALID, "velocity fabs need dim components");
+    MX_TRY(check_cover(geom, uold, 0, -1, "uold"));
+    MX_TRY(check_cover(geom, unew, 0, -1, "unew"));
+    MX_TRY(check_cover(geom, force, 0, -1, "force"));
+    MX_TRY(require_device());
+    Session S(stream);
+    DFab uo, un, fo, sp, w0c, um[3], ue[3], wm[3];
+    memset(&sp, 0, sizeof(sp));
+    memset(&w0c, 0, sizeof(w0c));
+    MX_TRY(S.fab(uold, &uo, 0, dim, true, false));
+    MX_TRY(S.fab(unew, &un, 0, dim, true, true));
+    MX_TRY(S.fab(force, &fo, 0, dim, true, false));
+    if (do_sponge) {
+        MX_TRY(check_cover(geom, sponge, 0, -1, "sponge"));
+        MX_TRY(S.fab(sponge, &sp, 0, 1, true, false));
+    }
+    for (int d = 0; d < dim; ++d) {
+        MX_TRY(check_cover(geom, &umac[d], 0, d, "umac"));
+        MX_TRY(check_cover(geom, &uedge[d], 0, d, "uedge"));
+        if (uedge[d].ncomp < dim) return fail(MX_ERR_INVALID, "uedge needs dim components");
+        MX_TRY(S.fab(&umac[d], &um[d], 0, 1, true, false));
+        MX_TRY(S.fab(&uedge[d], &ue[d], 0, dim, true, false));
+        if (spherical) {
+            MX_TRY(check_cover(geom, &w0mac[d], 0, d, "w0mac"));
+            MX_TRY(S.fab(&w0mac[d], &wm[d], 0, 1, true, false));
+        }
+    }
+    if (!spherical) {
+        if (w0_cart->ncomp < dim) return fail(MX_ERR_INVALID, "w0_cart needs dim components");
+        const int last = dim - 1;
+        for (int d = 0; d < dim; ++d) {
+            const int ng = d == last ? 1 : 0;
+            if (w0_cart->lo[d] > geom->valid_lo[d] || w0_cart->hi[d] < geom->valid_hi[d] + ng)
+                return fail(MX_ERR_INVALID, "w0_cart needs one ghost cell in the last direction");
+        }
+        MX_TRY(S.fab(w0_cart, &w0c, last, 1, true, false));
+    }
+    cart_update_vel(make_kgeom(geom), uo, un, um, ue, fo, sp, w0c, wm, dt, do_sponge, spherical, S.stream());
+    return S.finish();
 }
 
 }  // extern "C"

@@ -31,9 +31,23 @@ bool do_2d_planar_octant = false, do_planar_invsq_grav = false, add_pb = false;
 Real base_cutoff_density = -1.0, dpdt_factor = 0.0, planar_invsq_mass = 0.0,
      grav_const = -1.5e10;
 bool do_sponge = false, do_eos_h_above_cutoff = true;
+int s0_interp_type = 3, w0_interp_type = 2, s0mac_interp_type = 1, w0mac_interp_type = 1;
+Real buoyancy_cutoff_factor = 5.0;
 }  // namespace maestro
 int Rho = 0, RhoH = 1, Temp = 2, Pi = 3, FirstSpec = 4, NumSpec = 3, Nscal = 7;
 
+#ifndef DRV_OVERLAY
+#if (AMREX_SPACEDIM == 2)
+IntVect Maestro::nodal_flag(1, 1);
+#else
+IntVect Maestro::nodal_flag(1, 1, 1);
+#endif
+// defined in Source/MaestroBaseStateGeometry.cpp, only reached with use_exact_base_state
+void Maestro::InitBaseStateMapSphr(const int, const MFIter&, const GpuArray<Real, AMREX_SPACEDIM>,
+                                   const GpuArray<Real, AMREX_SPACEDIM>) {
+    Abort("ref_driver: InitBaseStateMapSphr is not on the tested path");
+}
+#endif
 #if (AMREX_SPACEDIM == 2)
 IntVect Maestro::nodal_flag_x(1, 0);
 IntVect Maestro::nodal_flag_y(0, 1);
@@ -403,5 +417,236 @@ int DRV(update_scal)(const MxGeom* g, const MxFab* sold, const MxFab* snew, cons
     m.UpdateScal(so, sn, sf, fo, p->start_comp, p->num_comp, p0);
     return 0;
 }
+
+#ifndef DRV_OVERLAY
+// ==== the passes either side of the path: the reference's own
+// MaestroConvert.cpp / MaestroFill3dData.cpp / MaestroForce.cpp / MaestroAdvection.cpp ========
+namespace {
+// alias a fab whose ghost widths differ per side / direction: valid box = the fab's own box
+// shrunk by ng (uniform); used for fabs the driver owns the geometry of
+struct SphrGeom {
+    int nr_tab[1];
+    double dr_tab[1];
+    void attach(Maestro& m, const MxGeom* g, const MxSphr* S) {
+        maestro::spherical = S && S->spherical;
+        maestro::use_exact_base_state = false;
+        if (!S) return;
+        maestro::s0_interp_type = S->s0_interp_type;
+        maestro::w0_interp_type = S->w0_interp_type;
+        maestro::s0mac_interp_type = S->s0mac_interp_type;
+        maestro::w0mac_interp_type = S->w0mac_interp_type;
+        if (!S->spherical) return;
+        auto& bg = m.base_geom;
+        bg.max_radial_level = 0;
+        bg.finest_radial_level = 0;
+        bg.nr_fine = S->nr_fine;
+        bg.dr_fine = S->dr_fine;
+        nr_tab[0] = S->nr_fine;
+        dr_tab[0] = S->dr_fine;
+        bg.nr.init(nr_tab, 1, 1, 1);
+        bg.dr.init(dr_tab, 1, 1, 1);
+        bg.r_cc_loc.init(const_cast<double*>(S->r_cc_loc), 1, S->nr_fine, 1);
+        bg.r_edge_loc.init(const_cast<double*>(S->r_edge_loc), 1, S->nr_fine + 1, 1);
+        for (int d = 0; d < 3; ++d) m.center[d] = S->center[d];
+        m.geom[0].setProbLo(S->prob_lo);
+        // only read with use_exact_base_state, but its Array4 is formed unconditionally
+        m.cell_cc_to_r.resize(1);
+        m.cell_cc_to_r[0].define(m.grids[0], m.dmap[0], 1, 0);
+    }
+};
+void set_bcs_f(Maestro& m, int ncomp, int code_hi_last) {
+    // bcs_f: "first-order extrap" records; only the entries the tested members read matter
+    m.bcs_f.resize(ncomp);
+    for (auto& b : m.bcs_f)
+        for (int d = 0; d < DIM; ++d) {
+            b.setLo(d, BCType::foextrap);
+            b.setHi(d, d == DIM - 1 ? code_hi_last : BCType::foextrap);
+        }
+    m.bcs_u.resize(DIM);
+    m.bcs_s.resize(ncomp);
+}
+// alias with an explicit valid box (fabs whose ghost widths the MxGeom does not describe)
+void alias_ng(MultiFab& mf, const MxGeom* g, const MxFab* f, int nodal_dir, int ng) {
+    Box vb = valid_box(g);
+    if (nodal_dir >= 0) vb.surroundingNodes(nodal_dir);
+    for (int d = 0; d < DIM; ++d)
+        if (vb.lo[d] - f->lo[d] != ng || f->hi[d] - vb.hi[d] != ng)
+            Abort("ref_driver: fab box is not the valid box grown by the expected ghost width");
+    mf.alias(vb, f->ncomp, ng, f->p);
+}
+}  // namespace
+
+// Maestro::ConvertRhoXToX / ConvertRhoHToH, Source/MaestroConvert.cpp:64-114 (the FillPatch /
+// AverageDown tail is a no-op in the shim)
+int DRV(convert_by_rho)(const MxGeom* g, const MxFab* scal, int rho, int c0, int nc, int flag) {
+    Maestro m;
+    setup(m, g);
+    set_bcs_f(m, scal->ncomp, BCType::foextrap);
+    Vector<MultiFab> s(1);
+    alias(s[0], g, scal, -1);
+    Rho = rho;
+    if (nc == 1 && c0 != FirstSpec) {
+        RhoH = c0;
+        m.ConvertRhoHToH(s, flag != 0);
+    } else {
+        FirstSpec = c0;
+        NumSpec = nc;
+        m.ConvertRhoXToX(s, flag != 0);
+    }
+    return 0;
+}
+
+// Maestro::Put1dArrayOnCart (per-level body), Source/MaestroFill3dData.cpp:48
+int DRV(put_1d_array_on_cart)(const MxGeom* g, const MxBase* s0, int lev, const MxFab* s0_cart,
+                              int edge, int vec, const MxSphr* S) {
+    Maestro m;
+    setup(m, g);
+    SphrGeom sg;
+    sg.attach(m, g, S);
+    BaseState<Real> b;
+    fill_base(b, s0);
+    MultiFab mf;
+    alias(mf, g, s0_cart, -1);
+    if (lev != 0 && !maestro::spherical) Abort("ref_driver: one level only");
+    m.Put1dArrayOnCart(0, b, mf, edge != 0, vec != 0);
+    return 0;
+}
+
+// Maestro::PutInPertForm, Source/MaestroConvert.cpp:6
+int DRV(put_in_pert_form)(const MxGeom* g, const MxFab* scal, const MxBase* s0, int lev, int comp,
+                          int flag, const MxSphr* S) {
+    Maestro m;
+    setup(m, g);
+    SphrGeom sg;
+    sg.attach(m, g, S);
+    set_bcs_f(m, scal->ncomp, BCType::foextrap);
+    BaseState<Real> b;
+    fill_base(b, s0);
+    Vector<MultiFab> s(1);
+    alias(s[0], g, scal, -1);
+    (void)lev;
+    m.PutInPertForm(s, b, comp, 0, m.bcs_f, flag != 0);
+    return 0;
+}
+
+// Maestro::ModifyScalForce, Source/MaestroForce.cpp:261.  The shim's FillPatch is a no-op, so
+// the ghost cell of the reference's s0_edge_cart temporary above the top zone is filled here
+// the way FillPatch(bcs_f) would (one box covering the domain in the last direction): the
+// reference's Put1dArrayOnCart is wrapped for that one call.
+int DRV(modify_scal_force)(const MxGeom* g, const MxFab* scal_force, const MxFab* state,
+                           const MxFab* umac, const MxBase* s0_edge, int lev, const MxFab* s0_cart,
+                           const MxFab* w0_cart, const double* w0, int comp, int fullform,
+                           int bcf_hi, const MxSphr* S) {
+    Maestro m;
+    setup(m, g);
+    SphrGeom sg;
+    sg.attach(m, g, S);
+    set_bcs_f(m, state->ncomp, bcf_hi);
+    (void)lev;
+    Vector<MultiFab> f(1), st(1), s0c(1);
+    alias(f[0], g, scal_force, -1);
+    alias(st[0], g, state, -1);
+    alias(s0c[0], g, s0_cart, -1);
+    Vector<std::array<MultiFab, DIM>> um;
+    alias_faces(um, g, umac);
+    BaseState<Real> be;
+    fill_base(be, s0_edge);
+    m.w0_cart.resize(1);
+    if (w0_cart) alias(m.w0_cart[0], g, w0_cart, -1);
+    if (S && S->spherical) fill1(m.w0, w0, S->nr_fine + 1);
+    m.fillpatch_hi_code = bcf_hi;
+    m.ModifyScalForce(f, st, um, be, s0c, comp, m.bcs_s, fullform);
+    return 0;
+}
+
+// Maestro::Addw0, Source/MaestroFill3dData.cpp:357
+int DRV(addw0)(const MxGeom* g, const MxFab* uedge, const MxFab* w0mac, const MxBase* w0, int lev,
+               double mult, int spherical) {
+    Maestro m;
+    setup(m, g);
+    maestro::spherical = spherical != 0;
+    (void)lev;
+    Vector<std::array<MultiFab, DIM>> ue(1), wm;
+    // uedge carries one ghost cell (FillUmacGhost's), w0mac too
+    for (int d = 0; d < DIM; ++d) alias(ue[0][d], g, &uedge[d], d);
+    alias_faces(wm, g, spherical ? w0mac : nullptr);
+    if (w0) fill_base(m.w0, w0);
+    m.sold.resize(1);
+    m.sold[0].define(m.grids[0], m.dmap[0], 1, 0);
+    m.Addw0(ue, wm, mult);
+    return 0;
+}
+
+#if (AMREX_SPACEDIM == 3)
+// Maestro::MakeW0mac, Source/MaestroFill3dData.cpp:464
+int DRV(make_w0mac)(const MxGeom* g, const MxFab* w0mac, const MxFab* w0_cart, const double* w0,
+                    const MxSphr* S) {
+    Maestro m;
+    setup(m, g);
+    SphrGeom sg;
+    sg.attach(m, g, S);
+    Vector<std::array<MultiFab, DIM>> wm;
+    alias_faces(wm, g, w0mac);
+    m.w0_cart.resize(1);
+    if (w0_cart)
+        alias(m.w0_cart[0], g, w0_cart, -1);
+    else
+        m.w0_cart[0].define(m.grids[0], m.dmap[0], 3, 2);
+    fill1(m.w0, w0, S->nr_fine + 1);
+    m.MakeW0mac(wm);
+    return 0;
+}
+
+// Maestro::MakeS0mac, Source/MaestroFill3dData.cpp:712.  s0mac_interp_type 1 reads the 2-ghost
+// s0_cart temporary after FillPatch(bcs_f): the shim's FillPatch hook fills it by first-order
+// extrapolation (the reference's bcs_f fill at outflow faces).
+int DRV(make_s0mac)(const MxGeom* g, const MxBase* s0, const MxFab* s0mac, const MxSphr* S) {
+    Maestro m;
+    setup(m, g);
+    SphrGeom sg;
+    sg.attach(m, g, S);
+    set_bcs_f(m, 1, BCType::foextrap);
+    Vector<std::array<MultiFab, DIM>> sm;
+    alias_faces(sm, g, s0mac);
+    BaseState<Real> b;
+    fill_base(b, s0);
+    m.fillpatch_hi_code = BCType::foextrap;
+    m.MakeS0mac(b, sm);
+    return 0;
+}
+#endif
+
+// Maestro::UpdateVel, Source/MaestroAdvection.cpp:299
+int DRV(update_vel)(const MxGeom* g, const MxFab* uold, const MxFab* unew, const MxFab* umac,
+                    const MxFab* uedge, const MxFab* force, const MxFab* sponge, const MxFab* w0_cart,
+                    const MxFab* w0mac, double dt, int do_sponge, int spherical) {
+    Maestro m;
+    setup(m, g);
+    maestro::spherical = spherical != 0;
+    maestro::do_sponge = do_sponge != 0;
+    m.dt = dt;
+    m.uold.resize(1);
+    m.unew.resize(1);
+    alias(m.uold[0], g, uold, -1);
+    alias(m.unew[0], g, unew, -1);
+    Vector<MultiFab> fo(1), sp(1);
+    alias(fo[0], g, force, -1);
+    if (sponge)
+        alias(sp[0], g, sponge, -1);
+    else
+        sp[0].define(m.grids[0], m.dmap[0], 1, 0);
+    Vector<std::array<MultiFab, DIM>> um, ue, wm;
+    alias_faces(um, g, umac);
+    alias_faces(ue, g, uedge);
+    alias_faces(wm, g, spherical ? w0mac : nullptr);
+    m.w0_cart.resize(1);
+    if (w0_cart)
+        alias(m.w0_cart[0], g, w0_cart, -1);
+    else
+        m.w0_cart[0].define(m.grids[0], m.dmap[0], DIM, 1);
+    m.UpdateVel(um, ue, fo, sp, wm);
+    return 0;
+}
+#endif  // !DRV_OVERLAY
 
 }  // extern "C"

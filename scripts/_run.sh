@@ -1,1 +1,1 @@
-TAG=tma1 scripts/gpu.sh first 2>&1 | grep -v "^$" | tail -14
+timeout -k 10 900 python -m pytest tests/test_cart.py -x -q -m gpu 2>&1 | tail -15
