@@ -270,14 +270,25 @@ int mx_make_w0_planar(const MxW0Params* par, const double* w0_old, const double*
 /* Replaces Maestro::Makew0 -> Makew0Sphr (Source/MaestroMakew0.cpp:537-740) including the
  * calls it makes: MakeGravEdge, spherical branch (Source/MaestroMakeGrav.cpp:303-322) and
  * Tridiag (:942-969).  r_cc_loc (nr_fine) and r_edge_loc (nr_fine+1) are level 0 of
- * base_geom.r_cc_loc / r_edge_loc; etarho_ec has nr_fine+1 entries.  use_exact_base_state
- * (Makew0SphrIrreg) is not supported. */
+ * base_geom.r_cc_loc / r_edge_loc; etarho_ec has nr_fine+1 entries. */
 int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* Sbar,
                     const double* rho0_old, const double* rho0_new, const double* p0_old,
                     const double* p0_new, const double* gamma1bar_old,
                     const double* gamma1bar_new, const double* p0_minus_peosbar,
                     const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
                     const double* r_edge_loc, double* w0, double* w0_force, void* stream);
+
+/* Replaces Maestro::Makew0 -> Makew0SphrIrreg (Source/MaestroMakew0.cpp:742-940; spherical with
+ * use_exact_base_state: irregularly spaced radial bins).  Same arguments; par->dr is not read.
+ * w0_force(0): the reference evaluates r_edge_loc(0,-1) (an out-of-bounds read, :926); this
+ * library uses the first cell's own width there. */
+int mx_make_w0_sphr_irreg(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                          const double* rho0_old, const double* rho0_new, const double* p0_old,
+                          const double* p0_new, const double* gamma1bar_old,
+                          const double* gamma1bar_new, const double* p0_minus_peosbar,
+                          const double* etarho_cc, const double* etarho_ec,
+                          const double* r_cc_loc, const double* r_edge_loc, double* w0,
+                          double* w0_force, void* stream);
 
 /* ---- Maestro::UpdateScal ------------------------------------
  * Parameters read by the per-box body of Maestro::UpdateScal

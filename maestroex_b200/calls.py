@@ -117,10 +117,11 @@ class Calls:
 
     def make_w0_sphr(self, par, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new,
                      gamma1bar_old, gamma1bar_new, p0_minus_peosbar, etarho_cc, etarho_ec,
-                     r_cc_loc, r_edge_loc, w0, w0_force, stream: int = 0):
+                     r_cc_loc, r_edge_loc, w0, w0_force, stream: int = 0, irreg: bool = False):
+        """irreg: Makew0SphrIrreg (use_exact_base_state, Source/MaestroMakew0.cpp:742-940)"""
         p = par.c()
         v = self._vp
-        rc = self._fn("make_w0_sphr")(
+        rc = self._fn("make_w0_sphr_irreg" if irreg else "make_w0_sphr")(
             C.byref(p), v(w0_old), v(Sbar), v(rho0_old), v(rho0_new), v(p0_old), v(p0_new),
             v(gamma1bar_old), v(gamma1bar_new), v(p0_minus_peosbar), v(etarho_cc),
             v(etarho_ec), v(r_cc_loc), v(r_edge_loc), v(w0), v(w0_force), *self._tail(stream))

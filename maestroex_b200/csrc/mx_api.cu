@@ -1048,13 +1048,15 @@ int mx_make_w0_planar(const MxW0Params* par, const double* w0_old, const double*
     return MX_OK;
 }
 
-int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* Sbar,
+static int make_w0_sphr_impl(bool irreg, const MxW0Params* par, const double* w0_old, const double* Sbar,
                     const double* rho0_old, const double* rho0_new, const double* p0_old,
                     const double* p0_new, const double* gamma1bar_old,
                     const double* gamma1bar_new, const double* p0_minus_peosbar,
                     const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
                     const double* r_edge_loc, double* w0, double* w0_force, void* stream) {
     MX_TRY(check_w0_params(par));
+    if (irreg && par->base_cutoff_density_coord + 1 > par->nr_fine)
+        return fail(MX_ERR_INVALID, "Makew0SphrIrreg: base_cutoff_density_coord + 1 exceeds nr_fine");
     MX_TRY(require_device());
     Session S(stream);
     const size_t nr = (size_t)par->nr_fine;
@@ -1081,7 +1083,7 @@ int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* S
     CUDA_OK(S.alloc(&st, sizeof(int)));
     w0_sphr(*par, d_w0o, d_S, d_r0o, d_r0n, d_p0o, d_p0n, d_g1o, d_g1n, d_pmp, d_ecc, d_eec,
             d_rcc, d_re, const_cast<double*>(d_w0), const_cast<double*>(d_f),
-            static_cast<double*>(scratch), static_cast<int*>(st), S.stream());
+            static_cast<double*>(scratch), static_cast<int*>(st), irreg, S.stream());
     CUDA_OK(cudaGetLastError());
     int status = 0;
     CUDA_OK(cudaMemcpyAsync(&status, st, sizeof(int), cudaMemcpyDeviceToHost, S.stream()));
@@ -1092,6 +1094,28 @@ int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* S
     if (status == 1) return fail(MX_ERR_INVALID, "tridiag: CAN NOT HAVE B(0) = 0.0");
     if (status == 2) return fail(MX_ERR_INVALID, "tridiag: TRIDIAG FAILED");
     return MX_OK;
+}
+
+int mx_make_w0_sphr(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                    const double* rho0_old, const double* rho0_new, const double* p0_old,
+                    const double* p0_new, const double* gamma1bar_old,
+                    const double* gamma1bar_new, const double* p0_minus_peosbar,
+                    const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
+                    const double* r_edge_loc, double* w0, double* w0_force, void* stream) {
+    return make_w0_sphr_impl(false, par, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, gamma1bar_old,
+                             gamma1bar_new, p0_minus_peosbar, etarho_cc, etarho_ec, r_cc_loc, r_edge_loc,
+                             w0, w0_force, stream);
+}
+
+int mx_make_w0_sphr_irreg(const MxW0Params* par, const double* w0_old, const double* Sbar,
+                          const double* rho0_old, const double* rho0_new, const double* p0_old,
+                          const double* p0_new, const double* gamma1bar_old,
+                          const double* gamma1bar_new, const double* p0_minus_peosbar,
+                          const double* etarho_cc, const double* etarho_ec, const double* r_cc_loc,
+                          const double* r_edge_loc, double* w0, double* w0_force, void* stream) {
+    return make_w0_sphr_impl(true, par, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, gamma1bar_old,
+                             gamma1bar_new, p0_minus_peosbar, etarho_cc, etarho_ec, r_cc_loc, r_edge_loc,
+                             w0, w0_force, stream);
 }
 
 // ---- Maestro::UpdateScal --------------------------------------------------------------

@@ -98,6 +98,10 @@ k_w0_planar(const MxW0Params P, const double* __restrict__ w0_old,
     w0_force_cells(P, w0_old, w0, w0_force);
 }
 
+// IRREG: Makew0SphrIrreg (use_exact_base_state, :742-940): the same algorithm with the local
+// spacings dr1 = r_edge(r) - r_edge(r-1), dr2 = r_edge(r+1) - r_edge(r), dr3 = r_cc(r) - r_cc(r-1)
+// in place of the uniform dr(0).
+template <bool IRREG>
 __global__ void __launch_bounds__(W0_THREADS, 1)
 k_w0_sphr(const MxW0Params P, const double* __restrict__ w0_old,
           const double* __restrict__ Sbar, const double* __restrict__ rho0_old,
@@ -137,11 +141,13 @@ k_w0_sphr(const MxW0Params P, const double* __restrict__ w0_old,
         g_nph[r] = gn;
         const double vd =
             rho0_old[r] > P.base_cutoff_density ? P.dpdt_factor * pmp[r] / P.dt_in : 0.0;
-        tS[r + 1] = dr0 * Sbar[r] * rcc[r] * rcc[r];
-        // the reference skips the subtraction when volume_discrepancy == 0; keep the skip as
-        // an explicit flag so that signed zeros come out the same
-        tV[r + 1] = (vd != 0.0) ? dr0 * vd * rcc[r] * rcc[r] / (gn * pn) : 0.0;
-        A[r + 1] = (vd != 0.0) ? 1.0 : 0.0;  // A is rebuilt below; borrowed as the flag array
+        const double dr1 = IRREG ? re[r + 1] - re[r] : dr0;  // :812 (cell r = reference index r-1)
+        tS[r + 1] = dr1 * Sbar[r] * rcc[r] * rcc[r];
+        // the regular routine skips the subtraction when volume_discrepancy == 0; keep the skip
+        // as an explicit flag so that signed zeros come out the same (the irregular one always
+        // subtracts, :813-817)
+        tV[r + 1] = (IRREG || vd != 0.0) ? dr1 * vd * rcc[r] * rcc[r] / (gn * pn) : 0.0;
+        A[r + 1] = (IRREG || vd != 0.0) ? 1.0 : 0.0;  // A is rebuilt below; borrowed as the flag array
         const bool dense = rn > P.base_cutoff_density;
         tM[r + 1] = dense ? 4.0 / 3.0 * kPi * (re[r + 1] - re[r]) *
                                 (re[r + 1] * re[r + 1] + re[r + 1] * re[r] + re[r] * re[r]) * rn
@@ -179,23 +185,43 @@ k_w0_sphr(const MxW0Params P, const double* __restrict__ w0_old,
         u[r] = 0.0;
     }
     __syncthreads();
-    // :653-681 matrix rows 1 .. max_cutoff
+    // :653-681 (regular) / :843-878 (irregular) matrix rows 1 .. max_cutoff
     for (int r = 1 + threadIdx.x; r <= max_cutoff; r += blockDim.x) {
-        double a = g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]);
-        a /= dr0 * dr0;
-        double b = -(g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]) +
-                     g_nph[r] * p_nph[r] / (rcc[r] * rcc[r])) /
-                   (dr0 * dr0);
-        const double dpdr = (p_nph[r] - p_nph[r - 1]) / dr0;
-        b -= 4.0 * dpdr / (re[r] * re[r] * re[r]);
-        double c = g_nph[r] * p_nph[r] / (rcc[r] * rcc[r]);
-        c /= dr0 * dr0;
-        const double f =
-            4.0 * dpdr * wS[r] / re[r] -
-            grav[r] *
-                (rcc[r] * rcc[r] * etarho_cc[r] - rcc[r - 1] * rcc[r - 1] * etarho_cc[r - 1]) /
-                (dr0 * re[r] * re[r]) -
-            4.0 * kPi * kGconst * 0.5 * (rho_nph[r] + rho_nph[r - 1]) * etarho_ec[r];
+        double a, b, c, f;
+        if (IRREG) {
+            const double dr1 = re[r] - re[r - 1];
+            const double dr2 = re[r + 1] - re[r];
+            const double dr3 = rcc[r] - rcc[r - 1];
+            a = g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]);
+            a /= dr1 * dr3;
+            b = -(g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1] * dr1) +
+                  g_nph[r] * p_nph[r] / (rcc[r] * rcc[r] * dr2)) /
+                dr3;
+            const double dpdr = (p_nph[r] - p_nph[r - 1]) / dr3;
+            b -= 4.0 * dpdr / (re[r] * re[r] * re[r]);
+            c = g_nph[r] * p_nph[r] / (rcc[r] * rcc[r]);
+            c /= dr2 * dr3;
+            f = 4.0 * dpdr * wS[r] / re[r] -
+                grav[r] *
+                    (rcc[r] * rcc[r] * etarho_cc[r] - rcc[r - 1] * rcc[r - 1] * etarho_cc[r - 1]) /
+                    (dr3 * re[r] * re[r]) -
+                4.0 * kPi * kGconst * 0.5 * (rho_nph[r] + rho_nph[r - 1]) * etarho_ec[r];
+        } else {
+            a = g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]);
+            a /= dr0 * dr0;
+            b = -(g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]) +
+                  g_nph[r] * p_nph[r] / (rcc[r] * rcc[r])) /
+                (dr0 * dr0);
+            const double dpdr = (p_nph[r] - p_nph[r - 1]) / dr0;
+            b -= 4.0 * dpdr / (re[r] * re[r] * re[r]);
+            c = g_nph[r] * p_nph[r] / (rcc[r] * rcc[r]);
+            c /= dr0 * dr0;
+            f = 4.0 * dpdr * wS[r] / re[r] -
+                grav[r] *
+                    (rcc[r] * rcc[r] * etarho_cc[r] - rcc[r - 1] * rcc[r - 1] * etarho_cc[r - 1]) /
+                    (dr0 * re[r] * re[r]) -
+                4.0 * kPi * kGconst * 0.5 * (rho_nph[r] + rho_nph[r - 1]) * etarho_ec[r];
+        }
         A[r] = a;
         B[r] = b;
         Cc[r] = c;
@@ -255,7 +281,24 @@ k_w0_sphr(const MxW0Params P, const double* __restrict__ w0_old,
         }
     }
     __syncthreads();
-    w0_force_cells(P, w0_old, w0, w0_force);
+    if (IRREG) {
+        // :924-938: the local spacing is that of the cell BELOW (r_edge(r) - r_edge(r-1)); for
+        // r = 0 the reference reads r_edge_loc(0,-1), out of bounds: the first cell's own width
+        // is used here and tests do not compare w0_force(0)
+        const double dt_in = P.dt_in, dtold_in = P.dtold_in;
+        const double dt_avg = 0.5 * (dt_in + dtold_in);
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+            const double dr1 = r > 0 ? re[r] - re[r - 1] : re[1] - re[0];
+            const double w0_old_cen = 0.5 * (w0_old[r] + w0_old[r + 1]);
+            const double w0_new_cen = 0.5 * (w0[r] + w0[r + 1]);
+            const double w0_avg = 0.5 * (dt_in * w0_old_cen + dtold_in * w0_new_cen) / dt_avg;
+            const double div_avg =
+                0.5 * (dt_in * (w0_old[r + 1] - w0_old[r]) + dtold_in * (w0[r + 1] - w0[r])) / dt_avg;
+            w0_force[r] = (w0_new_cen - w0_old_cen) / dt_avg + w0_avg * div_avg / dr1;
+        }
+    } else {
+        w0_force_cells(P, w0_old, w0, w0_force);
+    }
 }
 
 }  // namespace
@@ -276,9 +319,14 @@ void w0_sphr(const MxW0Params& P, const double* w0_old, const double* Sbar,
              const double* p0_new, const double* g1o, const double* g1n, const double* pmp,
              const double* etarho_cc, const double* etarho_ec, const double* rcc,
              const double* re, double* w0, double* w0_force, double* scratch, int* status_dev,
-             cudaStream_t stream) {
-    k_w0_sphr<<<1, W0_THREADS, 0, stream>>>(P, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new,
-                                           g1o, g1n, pmp, etarho_cc, etarho_ec, rcc, re, w0,
-                                           w0_force, scratch, status_dev);
+             bool irreg, cudaStream_t stream) {
+    if (irreg)
+        k_w0_sphr<true><<<1, W0_THREADS, 0, stream>>>(P, w0_old, Sbar, rho0_old, rho0_new, p0_old,
+                                                     p0_new, g1o, g1n, pmp, etarho_cc, etarho_ec, rcc,
+                                                     re, w0, w0_force, scratch, status_dev);
+    else
+        k_w0_sphr<false><<<1, W0_THREADS, 0, stream>>>(P, w0_old, Sbar, rho0_old, rho0_new, p0_old,
+                                                      p0_new, g1o, g1n, pmp, etarho_cc, etarho_ec, rcc,
+                                                      re, w0, w0_force, scratch, status_dev);
     mx_count_launch();
 }

@@ -15,5 +15,5 @@ void w0_sphr(const MxW0Params& P, const double* w0_old, const double* Sbar,
              const double* p0_new, const double* g1o, const double* g1n, const double* pmp,
              const double* etarho_cc, const double* etarho_ec, const double* rcc,
              const double* re, double* w0, double* w0_force, double* scratch, int* status_dev,
-             cudaStream_t stream);
+             bool irreg, cudaStream_t stream);
 #endif

@@ -1,8 +1,9 @@
 // Overlay for Source/MaestroMakew0.cpp: Maestro::Makew0 (Source/Maestro.H:1185-1196) and the
 // members that file defines, on libmxadv.so (mx_make_w0_planar / mx_make_w0_sphr).
-// One radial level (base_geom.max_radial_level == 0): the multilevel restriction / offset of
-// Makew0Planar (MaestroMakew0.cpp:185-236), Makew0PlanarVarg and Makew0SphrIrreg are not on the
-// accelerated path and abort here (reference convention for illegal states; no CPU fallback).
+// (mx_make_w0_planar / mx_make_w0_sphr / mx_make_w0_sphr_irreg).  One radial level
+// (base_geom.max_radial_level == 0): the multilevel restriction / offset of Makew0Planar
+// (MaestroMakew0.cpp:185-236) and Makew0PlanarVarg are not on the accelerated path and abort
+// here (reference convention for illegal states; no CPU fallback).
 #include <MxadvAmrex.H>
 
 using namespace amrex;
@@ -133,15 +134,29 @@ void Maestro::Makew0PlanarVarg(const BaseState<Real>&, BaseState<Real>&, const B
     Abort("libmxadv: Makew0PlanarVarg (do_planar_invsq_grav / do_2d_planar_octant) is not supported");
 }
 
-void Maestro::Makew0SphrIrreg(const BaseState<Real>&, BaseState<Real>&, const BaseState<Real>&,
-                              const BaseState<Real>&, const BaseState<Real>&,
-                              const BaseState<Real>&, const BaseState<Real>&,
-                              const BaseState<Real>&, const BaseState<Real>&,
-                              const BaseState<Real>&, const Real, const Real) {
-    Abort("libmxadv: Makew0SphrIrreg (use_exact_base_state) is not supported");
+void Maestro::Makew0SphrIrreg(const BaseState<Real>& w0_old, BaseState<Real>& w0_force,
+                              const BaseState<Real>& Sbar_in, const BaseState<Real>& rho0_old_in,
+                              const BaseState<Real>& rho0_new_in, const BaseState<Real>& p0_old_in,
+                              const BaseState<Real>& p0_new_in,
+                              const BaseState<Real>& gamma1bar_old_in,
+                              const BaseState<Real>& gamma1bar_new_in,
+                              const BaseState<Real>& p0_minus_peosbar, const Real dt_in,
+                              const Real dtold_in) {
+    BL_PROFILE_VAR("Maestro::Makew0SphrIrreg()", Makew0SphrIrreg);
+    const MxW0Params p = w0_params(base_geom, dt, dt_in, dtold_in, true);
+    mxadv::check(mx_make_w0_sphr_irreg(&p, row0(w0_old), row0(Sbar_in), row0(rho0_old_in),
+                                       row0(rho0_new_in), row0(p0_old_in), row0(p0_new_in),
+                                       row0(gamma1bar_old_in), row0(gamma1bar_new_in),
+                                       row0(p0_minus_peosbar), row0(etarho_cc), row0(etarho_ec),
+                                       base_geom.r_cc_loc.dataPtr(), base_geom.r_edge_loc.dataPtr(),
+                                       row0(w0), row0(w0_force), mxadv::stream()),
+                 "Makew0SphrIrreg");
+#ifdef AMREX_USE_CUDA
+    Gpu::streamSynchronize();  // w0 / w0_force (managed memory) are read on the host next
+#endif
 }
 
-// Only the two unsupported variants above called these (MaestroMakew0.cpp:322-330,:469,:905);
+// Only the host variants called these (MaestroMakew0.cpp:322-330,:469,:905);
 // they stay defined so that the set of symbols this translation unit provides is unchanged.
 void Maestro::Tridiag(const BaseStateArray<Real>&, const BaseStateArray<Real>&,
                       const BaseStateArray<Real>&, const BaseStateArray<Real>&,

@@ -266,6 +266,10 @@ W0_CASES = {
     "sphr_cut_above": (1, 64, 80, 1, 0, 0.3, 1.0e5, 7),
     "sphr_odd": (1, 257, 200, 1, 0, 0.5, 3.0e4, 8),
     "sphr_wd": (1, 2218, 1800, 1, 0, 0.2, 1.0e4, 9),
+    # spherical == 2: use_exact_base_state (Makew0SphrIrreg), irregular radial bins
+    "irreg_small": (2, 64, 50, 1, 0, 0.0, 1.0e4, 10),
+    "irreg_odd": (2, 257, 200, 1, 0, 0.5, 3.0e4, 11),
+    "irreg_wd": (2, 2218, 1800, 1, 0, 0.2, 1.0e4, 12),
 }
 
 
@@ -294,11 +298,19 @@ def make_w0_problem(name: str):
         "r_cc_loc": (np.arange(nr) + 0.5) * dr,
         "r_edge_loc": np.arange(nr + 1) * dr,
     }
+    if sph == 2:
+        # the bins of the exact base state (Source/MaestroBaseStateGeometry... init: one bin per
+        # distinct cell-centre radius): r_cc = sqrt(0.75 + 2 r) dx, edges half way in r^2
+        dxf = 5.0e8 / np.sqrt(0.75 + 2.0 * nr)
+        d["r_cc_loc"] = np.sqrt(0.75 + 2.0 * np.arange(nr)) * dxf
+        e = np.sqrt(0.75 + 2.0 * (np.arange(nr + 1) - 0.5).clip(min=0.0)) * dxf
+        e[0] = 0.0
+        d["r_edge_loc"] = e
     d = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in d.items()}
     par = W0Params(nr_fine=nr, base_cutoff_density_coord=cut, dr=dr, dt=0.37, dt_in=0.4,
                    dtold_in=0.33, is_predictor=pred, add_pb=pb, dpdt_factor=dpdt,
                    base_cutoff_density=bcd)
-    return bool(sph), par, d
+    return int(sph), par, d
 
 
 def run_w0(calls, sph: bool, par, d, xp=np, put=lambda a: a):
@@ -312,7 +324,7 @@ def run_w0(calls, sph: bool, par, d, xp=np, put=lambda a: a):
         calls.make_w0_sphr(par, a["w0_old"], a["Sbar"], a["rho0_old"], a["rho0_new"],
                            a["p0_old"], a["p0_new"], a["gamma1bar_old"], a["gamma1bar_new"],
                            a["p0_minus_peosbar"], a["etarho_cc"], a["etarho_ec"],
-                           a["r_cc_loc"], a["r_edge_loc"], w0, force)
+                           a["r_cc_loc"], a["r_edge_loc"], w0, force, irreg=(sph == 2))
         pb = 0.0
     else:
         pb = calls.make_w0_planar(par, a["w0_old"], a["Sbar"], a["p0_old"], a["p0_new"],

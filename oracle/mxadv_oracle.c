@@ -1189,6 +1189,105 @@ int orc_make_w0_sphr(const MxW0Params* p, const double* w0_old, const double* Sb
     return 0;
 }
 
+/* Maestro::Makew0 -> Makew0SphrIrreg, Source/MaestroMakew0.cpp:742-940 (use_exact_base_state:
+ * irregular radial bins), with MakeGravEdge's spherical branch and Tridiag inlined.
+ * w0_force(0): the reference reads r_edge_loc(0,-1) (out of bounds, :926); the first cell's own
+ * width stands in here and is not compared by the tests. */
+int orc_make_w0_sphr_irreg(const MxW0Params* p, const double* w0_old, const double* Sbar,
+                     const double* rho0_old, const double* rho0_new, const double* p0_old,
+                     const double* p0_new, const double* g1o, const double* g1n,
+                     const double* pmp, const double* etarho_cc, const double* etarho_ec,
+                     const double* rcc, const double* re, double* w0, double* w0_force) {
+    const double Gconst = 6.67428e-8; /* Source/Maestro.H:1864 */
+    const int nr = p->nr_fine;
+    const double dt_in = p->dt_in;
+    double* buf = (double*)calloc((size_t)(11 * (nr + 2)), sizeof(double));
+    double *g_nph = buf, *p_nph = g_nph + nr + 2, *rho_nph = p_nph + nr + 2,
+           *wS = rho_nph + nr + 2, *grav = wS + nr + 2, *A = grav + nr + 2, *B = A + nr + 2,
+           *C = B + nr + 2, *F = C + nr + 2, *u = F + nr + 2, *gam = u + nr + 2;
+    for (int r = 0; r < nr; ++r) { /* :595-600 */
+        p_nph[r] = 0.5 * (p0_old[r] + p0_new[r]);
+        rho_nph[r] = 0.5 * (rho0_old[r] + rho0_new[r]);
+        g_nph[r] = 0.5 * (g1o[r] + g1n[r]);
+    }
+    wS[0] = 0.0;
+    for (int r = 1; r <= nr; ++r) { /* :608-622 */
+        double volume_discrepancy = rho0_old[r - 1] > p->base_cutoff_density
+                                        ? p->dpdt_factor * pmp[r - 1] / dt_in
+                                        : 0.0;
+        double dr1 = re[r] - re[r - 1];
+        wS[r] = wS[r - 1] + dr1 * Sbar[r - 1] * rcc[r - 1] * rcc[r - 1] -
+                dr1 * volume_discrepancy * rcc[r - 1] * rcc[r - 1] / (g_nph[r - 1] * p_nph[r - 1]);
+    }
+    for (int r = 1; r <= nr; ++r) wS[r] /= (re[r] * re[r]);
+    /* MakeGravEdge, spherical */
+    grav[0] = 0.0;
+    double mencl = 0.0;
+    for (int r = 1; r <= nr; ++r) {
+        if (rho_nph[r - 1] > p->base_cutoff_density) {
+            mencl += 4.0 / 3.0 * M_PI * (re[r] - re[r - 1]) *
+                     (re[r] * re[r] + re[r] * re[r - 1] + re[r - 1] * re[r - 1]) * rho_nph[r - 1];
+        }
+        grav[r] = -Gconst * mencl / (re[r] * re[r]);
+    }
+    int max_cutoff = p->base_cutoff_density_coord < nr - 1 ? p->base_cutoff_density_coord : nr - 1;
+    for (int r = 1; r <= max_cutoff; ++r) { /* :843-878 */
+        double dr1 = re[r] - re[r - 1];
+        double dr2 = re[r + 1] - re[r];
+        double dr3 = rcc[r] - rcc[r - 1];
+        A[r] = g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1]);
+        A[r] /= dr1 * dr3;
+        B[r] = -(g_nph[r - 1] * p_nph[r - 1] / (rcc[r - 1] * rcc[r - 1] * dr1) +
+                 g_nph[r] * p_nph[r] / (rcc[r] * rcc[r] * dr2)) /
+               dr3;
+        double dpdr = (p_nph[r] - p_nph[r - 1]) / dr3;
+        B[r] -= 4.0 * dpdr / (re[r] * re[r] * re[r]);
+        C[r] = g_nph[r] * p_nph[r] / (rcc[r] * rcc[r]);
+        C[r] /= dr2 * dr3;
+        F[r] = 4.0 * dpdr * wS[r] / re[r] -
+               grav[r] *
+                   (rcc[r] * rcc[r] * etarho_cc[r] - rcc[r - 1] * rcc[r - 1] * etarho_cc[r - 1]) /
+                   (dr3 * re[r] * re[r]) -
+               4.0 * M_PI * Gconst * 0.5 * (rho_nph[r] + rho_nph[r - 1]) * etarho_ec[r];
+    }
+    A[0] = 0.0; B[0] = 1.0; C[0] = 0.0; F[0] = 0.0;
+    A[max_cutoff + 1] = -1.0; B[max_cutoff + 1] = 1.0; C[max_cutoff + 1] = 0.0;
+    F[max_cutoff + 1] = 0.0;
+    { /* Tridiag(A, B, C, F, u, max_cutoff + 2) */
+        const int n = max_cutoff + 2;
+        if (B[0] == 0) { free(buf); return -1; }
+        double bet = B[0];
+        u[0] = F[0] / bet;
+        for (int j = 1; j < n; j++) {
+            gam[j] = C[j - 1] / bet;
+            bet = B[j] - A[j] * gam[j];
+            if (bet == 0) { free(buf); return -1; }
+            u[j] = (F[j] - A[j] * u[j - 1]) / bet;
+        }
+        for (int j = n - 2; j >= 0; --j) u[j] -= gam[j + 1] * u[j + 1];
+    }
+    w0[0] = wS[0];
+    for (int r = 1; r <= max_cutoff + 1; ++r) w0[r] = u[r] / (re[r] * re[r]) + wS[r];
+    for (int r = max_cutoff + 2; r <= nr; ++r) {
+        w0[r] = w0[max_cutoff + 1] * re[max_cutoff + 1] * re[max_cutoff + 1] / (re[r] * re[r]);
+    }
+    { /* :924-938 */
+        const double dtold_in = p->dtold_in;
+        const double dt_avg = 0.5 * (dt_in + dtold_in);
+        for (int r = 0; r < nr; ++r) {
+            double dr1 = r > 0 ? re[r] - re[r - 1] : re[1] - re[0];
+            double w0_old_cen = 0.5 * (w0_old[r] + w0_old[r + 1]);
+            double w0_new_cen = 0.5 * (w0[r] + w0[r + 1]);
+            double w0_avg = 0.5 * (dt_in * w0_old_cen + dtold_in * w0_new_cen) / dt_avg;
+            double div_avg =
+                0.5 * (dt_in * (w0_old[r + 1] - w0_old[r]) + dtold_in * (w0[r + 1] - w0[r])) / dt_avg;
+            w0_force[r] = (w0_new_cen - w0_old_cen) / dt_avg + w0_avg * div_avg / dr1;
+        }
+    }
+    free(buf);
+    return 0;
+}
+
 /* Maestro::UpdateScal, zone loop of one box: Source/MaestroAdvection.cpp:86-251.  The EOS call
  * (:137-159, third-party Microphysics) is not restated: those zones are flagged in eos_mask. */
 static inline long fidx(const MxFab* f, int i, int j, int k) {

@@ -326,7 +326,7 @@ void fill1(BaseState<Real>& b, const double* src, int len) {
     for (int i = 0; i < len; ++i) a(i) = src ? src[i] : 0.0;
 }
 
-int run_w0(bool sphr, const MxW0Params* p, const double* w0_old, const double* Sbar,
+int run_w0(int sphr, const MxW0Params* p, const double* w0_old, const double* Sbar,
            const double* rho0_old, const double* rho0_new, const double* p0_old,
            const double* p0_new, const double* g1o, const double* g1n, const double* pmp,
            const double* etarho_cc, const double* etarho_ec, const double* r_cc,
@@ -335,8 +335,8 @@ int run_w0(bool sphr, const MxW0Params* p, const double* w0_old, const double* S
     W0Geom wg;
     wg.attach(m, p, r_cc, r_edge);
     const int nr = p->nr_fine;
-    maestro::spherical = sphr;
-    maestro::use_exact_base_state = false;
+    maestro::spherical = sphr != 0;
+    maestro::use_exact_base_state = sphr == 2;  // Makew0SphrIrreg
     maestro::do_planar_invsq_grav = false;
     maestro::do_2d_planar_octant = false;
     maestro::maestro_verbose = 0;
@@ -375,7 +375,7 @@ int DRV(make_w0_planar)(const MxW0Params* p, const double* w0_old, const double*
                        const double* p0_old, const double* p0_new, const double* g1o,
                        const double* g1n, const double* pmp, const double* etarho_cc,
                        double* w0, double* w0_force, double* p0bdot) {
-    return run_w0(false, p, w0_old, Sbar, nullptr, nullptr, p0_old, p0_new, g1o, g1n, pmp,
+    return run_w0(0, p, w0_old, Sbar, nullptr, nullptr, p0_old, p0_new, g1o, g1n, pmp,
                   etarho_cc, nullptr, nullptr, nullptr, w0, w0_force, p0bdot);
 }
 
@@ -385,7 +385,17 @@ int DRV(make_w0_sphr)(const MxW0Params* p, const double* w0_old, const double* S
                      const double* p0_new, const double* g1o, const double* g1n,
                      const double* pmp, const double* etarho_cc, const double* etarho_ec,
                      const double* r_cc, const double* r_edge, double* w0, double* w0_force) {
-    return run_w0(true, p, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, g1o, g1n, pmp,
+    return run_w0(1, p, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, g1o, g1n, pmp,
+                  etarho_cc, etarho_ec, r_cc, r_edge, w0, w0_force, nullptr);
+}
+
+// Maestro::Makew0 -> Makew0SphrIrreg (use_exact_base_state), Source/MaestroMakew0.cpp:5,742
+int DRV(make_w0_sphr_irreg)(const MxW0Params* p, const double* w0_old, const double* Sbar,
+                           const double* rho0_old, const double* rho0_new, const double* p0_old,
+                           const double* p0_new, const double* g1o, const double* g1n,
+                           const double* pmp, const double* etarho_cc, const double* etarho_ec,
+                           const double* r_cc, const double* r_edge, double* w0, double* w0_force) {
+    return run_w0(2, p, w0_old, Sbar, rho0_old, rho0_new, p0_old, p0_new, g1o, g1n, pmp,
                   etarho_cc, etarho_ec, r_cc, r_edge, w0, w0_force, nullptr);
 }
 

@@ -95,6 +95,8 @@ def main():
     for name in W0_CASES:
         sph, par, d = make_w0_problem(name)
         w0, force, pb = run_w0(ref, sph, par, d)
+        if name.startswith("irreg"):
+            force[0] = 0.0  # undefined in the reference (out-of-bounds read, :926): not compared
         np.savez_compressed(os.path.join(HERE, "w0_" + name + ".npz"), w0=w0, w0_force=force,
                             p0bdot=np.float64(pb), **{"in_" + k: v for k, v in d.items()})
         print("w0", name, "ok")

@@ -21,9 +21,16 @@ def golden(name):
     return sph, par, d, z
 
 
-def check(z, w0, force, pb):
+def f0(name):
+    """first w0_force entry that is compared: Makew0SphrIrreg reads r_edge_loc(0,-1) for cell 0
+    (an out-of-bounds read in the reference, Source/MaestroMakew0.cpp:926), so its w0_force(0)
+    is not defined by the reference"""
+    return 1 if name.startswith("irreg") else 0
+
+
+def check(z, w0, force, pb, name=""):
     assert np.array_equal(w0, z["w0"])
-    assert np.array_equal(force, z["w0_force"])
+    assert np.array_equal(force[f0(name):], z["w0_force"][f0(name):])
     assert pb == float(z["p0bdot"])
 
 
@@ -34,14 +41,14 @@ def test_oracle_vs_reference(oracle_calls, ref3d, name):
     ow, of, opb = run_w0(oracle_calls, sph, par, d)
     assert np.isfinite(rw).all() and np.abs(rw).max() > 0.0
     assert np.array_equal(rw, ow)
-    assert np.array_equal(rf, of)
+    assert np.array_equal(rf[f0(name):], of[f0(name):])
     assert rpb == opb
 
 
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_matches_golden(oracle_calls, name):
     sph, par, d, z = golden(name)
-    check(z, *run_w0(oracle_calls, sph, par, d))
+    check(z, *run_w0(oracle_calls, sph, par, d), name=name)
 
 
 def test_planar_closed_box_property(oracle_calls):
@@ -66,7 +73,7 @@ def test_gpu_matches_golden_and_oracle(oracle_calls, name, residency):
     assert mxlib.load().mx_launch_count() == 1
     if residency == "device":
         w0, force = w0.cpu().numpy(), force.cpu().numpy()
-    check(z, w0, force, pb)
+    check(z, w0, force, pb, name=name)
     ow, of, opb = run_w0(oracle_calls, sph, par, d)
     assert np.array_equal(w0, ow) and np.array_equal(force, of) and pb == opb
 
@@ -86,7 +93,7 @@ def test_gpu_tridiag_failure_is_reported():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["planar_corr_pb", "planar_wd", "sphr_odd", "sphr_wd"])
+@pytest.mark.parametrize("name", ["planar_corr_pb", "planar_wd", "sphr_odd", "sphr_wd", "irreg_odd"])
 def test_overlay_makew0(oracle_calls, name):
     """maestroex_b200/overlay/MaestroMakew0.cpp (Maestro::Makew0 on libmxadv.so) driven like
     the compiled reference."""
@@ -95,4 +102,4 @@ def test_overlay_makew0(oracle_calls, name):
     if ovl is None:
         pytest.skip("oracle/_ref/libmxadv_overlay3d.so not built")
     sph, par, d, z = golden(name)
-    check(z, *run_w0(ovl, sph, par, d))
+    check(z, *run_w0(ovl, sph, par, d), name=name)
