@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-halo", action="store_true", help="N>1: skip the ghost exchange")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p", "py"],
+                    help="N>1 ghost exchange: mx_halo_exchange of libmxadv.so over NCCL send/recv "
+                         "(default) or NVLink peer stores, or the round-1 Python/torch.distributed "
+                         "loop around mx_halo_pack/unpack (A/B only)")
     return ap.parse_args()
 
 
@@ -195,7 +199,8 @@ def run_mxadv(a):
 
     from maestroex_b200 import lib as mxlib
     from maestroex_b200.devsynth import make_device_problem, to_pinned_host
-    from maestroex_b200.fusedcalls import density_edge_flux, enthalpy_edge_flux
+    from maestroex_b200.fusedcalls import (density_edge_flux, enthalpy_edge_flux,
+                                           enthalpy_edge_flux_sph)
     from maestroex_b200.synth import FIRSTSPEC, RHO, RHOH
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,7 +216,8 @@ def run_mxadv(a):
     calls = mxlib.calls()
     ng = 4 if a.ppm == 2 else 3
     n = a.n
-    from maestroex_b200.decomp import Brick, DevicePacker, HaloExchanger, rank_grid
+    from maestroex_b200.decomp import (Brick, DevicePacker, HaloExchanger, LibExchanger,
+                                       rank_grid)
     pg = rank_grid(world)
     brick = Brick(rank, pg)
     coord = brick.coord
@@ -229,33 +235,41 @@ def run_mxadv(a):
     def enthalpy_pass():
         if not a.spherical:
             enthalpy_edge_flux(calls, prob, epar_h, fpar, outputs=outputs, stream=stream)
-            return
-        # spherical: the fused enthalpy entry point is planar only; the same two reference
-        # calls separately (MakeEdgeScal -> fused MODE-0 kernel, MakeRhoHFlux -> flux kernel)
-        b, m = prob.base, prob.mac
-        calls.make_edge_scal(prob.geom, prob.state, prob.sedge, prob.umac, prob.force, epar_h,
-                             stream)
-        calls.make_rhoh_flux(prob.geom, prob.sflux, prob.sedge, prob.umac, b["rho0_old"],
-                             b["rho0_edge_old"], m["r0mac_old"], b["rho0_new"],
-                             b["rho0_edge_new"], m["r0mac_new"], b["rhoh0_old"],
-                             b["rhoh0_edge_old"], None, b["rhoh0_new"], b["rhoh0_edge_new"],
-                             None, m["h0mac_old"], m["h0mac_new"], fpar, stream)
+        else:  # spherical flux forms read the base state from face arrays (r0mac / h0mac)
+            enthalpy_edge_flux_sph(calls, prob, epar_h, fpar, outputs=outputs, stream=stream)
 
+    # N > 1: the ghost cells of the swept components come from the face neighbours of the
+    # rank's brick.  Product path: mx_halo_exchange (include/mxadv.h) - topology, packing,
+    # transport and unpacking behind the C ABI.
     halo = None
+    dens_comps = [RHO] + list(range(FIRSTSPEC, FIRSTSPEC + a.nspec))
     if world > 1 and not a.no_halo:
-        halo = HaloExchanger(prob.geom, prob.state, prob.bc, brick, ng,
-                             DevicePacker(calls, dev))
+        if a.halo == "py":
+            halo = HaloExchanger(prob.geom, prob.state, prob.bc, brick, ng, DevicePacker(calls, dev))
+        else:
+            halo = LibExchanger(calls, rank, world, pg,
+                                transport=LibExchanger.P2P if a.halo == "p2p" else LibExchanger.NCCL,
+                                dist=dist, device=dev)
+    periodic = [int(prob.bc[RHO][d]) == 0 and int(prob.bc[RHO][3 + d]) == 0 for d in range(3)]
+
+    def exchange(comps):
+        if halo is None:
+            return
+        if a.halo == "py":
+            halo.exchange(comps, stream)
+            return
+        from maestroex_b200.decomp import contiguous_runs
+        for c0, nc in contiguous_runs(comps):
+            halo.exchange(prob.geom, prob.state, ng, c0, nc, periodic, stream)
 
     def step(ev=None):
-        if halo is not None:
-            halo.exchange([RHO] + list(range(FIRSTSPEC, FIRSTSPEC + a.nspec)), stream)
+        exchange(dens_comps)
         if ev is not None:
             ev[0].record()
         density_edge_flux(calls, prob, epar_d, fpar, outputs=outputs, stream=stream)
         if ev is not None:
             ev[1].record()
-        if halo is not None:
-            halo.exchange([RHOH], stream)
+        exchange([RHOH])
         enthalpy_pass()
 
     def barrier():
@@ -385,7 +399,7 @@ def run_mxadv(a):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded)",
             "config": {"workload": workload_name(a), "zones_per_gpu": zones,
                        "updates_per_step": updates_per_step, "rank_grid": list(pg),
-                       "halo_exchange": bool(halo is not None),
+                       "halo_exchange": (a.halo if halo is not None else False),
                        "l2": "inputs (>100 GB/step at 512^3) far exceed the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk.summary(),

@@ -404,7 +404,10 @@ int mx_halo_exchange(MxComm* c, const MxGeom* geom, const MxFab* fab, int ng, in
         n3[d] = ng;
         const size_t n = (size_t)n3[0] * n3[1] * n3[2] * ncomp;
         const int nbr[2] = {c->neighbour(d, 0, periodic[d] != 0), c->neighbour(d, 1, periodic[d] != 0)};
-        int rc = ensure_buffers(c, d, n, nbr, stream);
+        // P2P slab buffers are registered with the peers once: size them for ALL components of
+        // the fab, so that later exchanges of other component ranges of it fit
+        const size_t n_cap = c->transport == MX_HALO_P2P ? (size_t)n3[0] * n3[1] * n3[2] * fab->ncomp : n;
+        int rc = ensure_buffers(c, d, n_cap, nbr, stream);
         if (rc != MX_OK) return rc;
         if (c->transport == MX_HALO_NCCL) {
             for (int s = 0; s < 2; ++s)

@@ -8,7 +8,7 @@ from maestroex_b200.abi import Base, Fab
 
 def to_device(prob):
     import torch
-    dev = torch.device("cuda:0")
+    dev = torch.device("cuda", torch.cuda.current_device())  # one rank per GPU under torchrun
 
     def fab(f):
         return Fab(torch.from_numpy(np.ascontiguousarray(f.data)).to(dev), f.lo, f.hi)
