@@ -55,10 +55,11 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-halo", action="store_true", help="N>1: skip the ghost exchange")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p", "py"],
-                    help="N>1 ghost exchange: mx_halo_exchange of libmxadv.so over NCCL send/recv "
-                         "(default) or NVLink peer stores, or the round-1 Python/torch.distributed "
-                         "loop around mx_halo_pack/unpack (A/B only)")
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "py"],
+                    help="N>1 ghost exchange: mx_halo_exchange of libmxadv.so with NVLink peer stores "
+                         "(default: measured faster, 1.8 vs 3.8 ms per step at 8 x 512^3, "
+                         "profiles/r2_bench_n8_*) or NCCL send/recv, or the round-1 Python / "
+                         "torch.distributed loop around mx_halo_pack/unpack (A/B only)")
     return ap.parse_args()
 
 
@@ -249,7 +250,7 @@ def run_mxadv(a):
         else:
             halo = LibExchanger(calls, rank, world, pg,
                                 transport=LibExchanger.P2P if a.halo == "p2p" else LibExchanger.NCCL,
-                                dist=dist, device=dev)
+                                dist=dist, device=dev)  # raises if peer access is unavailable
     periodic = [int(prob.bc[RHO][d]) == 0 and int(prob.bc[RHO][3 + d]) == 0 for d in range(3)]
 
     def exchange(comps):
