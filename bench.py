@@ -346,48 +346,93 @@ def run_mxadv(a):
         he_d = hps[0].edge_params(FIRSTSPEC, a.nspec, ppm_type=a.ppm)
         he_h = hps[0].edge_params(RHOH, 1, ppm_type=a.ppm)
 
-        def e2e_worker(w):
+        from maestroex_b200.abi import Fab, UpdateParams
+        from maestroex_b200.fusedcalls import density_advance, enthalpy_advance
+        from maestroex_b200.synth import TEMP
+
+        # host-side outputs of the fused advances: snew (valid zones of the species / density /
+        # enthalpy components are written), the time-centred enthalpy force and the EOS mask
+        def pinned_like(f, fill):
+            t = torch.full(tuple(f.data.shape), fill, dtype=torch.float64).pin_memory()
+            return Fab(t, f.lo, f.hi)
+
+        hnew = [pinned_like(hp.state, 1.0) for hp in hps]
+        hfup = [pinned_like(hp.force, 0.0) for hp in hps]
+        hmask = [torch.zeros(en ** 3, dtype=torch.uint8).pin_memory() for _ in hps]
+        up_d = UpdateParams(dt=hps[0].dt, start_comp=FIRSTSPEC, num_comp=a.nspec, num_spec=a.nspec,
+                            base_cutoff_density=-1.0, rho_comp=RHO, rhoh_comp=RHOH, temp_comp=TEMP,
+                            first_spec=FIRSTSPEC)
+        up_h = UpdateParams(dt=hps[0].dt, start_comp=RHOH, num_comp=1, num_spec=a.nspec,
+                            base_cutoff_density=-1.0, rho_comp=RHO, rhoh_comp=RHOH, temp_comp=TEMP,
+                            first_spec=FIRSTSPEC)
+
+        def e2e_worker(w, fused):
             torch.cuda.set_device(local)
             hp, st = hps[w], streams[w].cuda_stream
             hout = (hp.sedge, hp.sflux, hp.etarhoflux)
             for _ in range(w, a.e2e_boxes, nthr):
-                density_edge_flux(calls, hp, he_d, fpar, outputs=hout, stream=st)
-                enthalpy_edge_flux(calls, hp, he_h, fpar, outputs=hout, stream=st)
+                if fused:
+                    # DensityAdvance / EnthalpyAdvance as overlay_fused calls them: edge states
+                    # and fluxes stay on the device, the new state comes back
+                    density_advance(calls, hp, hnew[w], he_d, fpar, up_d, species_force_is_zero=True,
+                                    outputs=hout, stream=st)
+                    enthalpy_advance(calls, hp, hnew[w], hfup[w], he_h, fpar, up_h, eos_mask=hmask[w],
+                                     stream=st)
+                else:
+                    density_edge_flux(calls, hp, he_d, fpar, outputs=hout, stream=st)
+                    enthalpy_edge_flux(calls, hp, he_h, fpar, outputs=hout, stream=st)
 
-        def e2e_step():
+        def e2e_step(fused):
             if nthr == 1:
-                e2e_worker(0)
+                e2e_worker(0, fused)
                 return
-            ths = [threading.Thread(target=e2e_worker, args=(w,)) for w in range(nthr)]
+            ths = [threading.Thread(target=e2e_worker, args=(w, fused)) for w in range(nthr)]
             for t_ in ths:
                 t_.start()
             for t_ in ths:
                 t_.join()
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        te = float(te[0]) / a.steps
+        def e2e_time(fused):
+            e2e_step(fused)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                e2e_step(fused)
+            torch.cuda.synchronize()
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te[0]) / a.steps
+
+        te_adv = e2e_time(True)
+        te_mem = e2e_time(False)
         C = a.nspec + 1
         cells_s = (en + 2 * ng) ** 3
         cells_f = (en + 2) ** 3
         face = (en + 1) * en * en
         uface = (en + 3) * (en + 2) ** 2
-        h2d = 8 * a.e2e_boxes * (C * cells_s + C * cells_f + 3 * uface + face      # density
-                                 + cells_s + cells_f + 3 * uface + 3 * face)  # enthalpy
-        d2h = 8 * a.e2e_boxes * (3 * C * face + 3 * C * face + face + 3 * face + 3 * face)
-        e2e = {"value": en ** 3 * (a.nspec + 2) * a.e2e_boxes * world / te, "unit": UNIT,
+        nb = a.e2e_boxes
+        # fused advances: converted state (C comps), force(Rho), 3 MAC velocities and etarhoflux
+        # up; snew(C, valid zones) and etarhoflux down | state(RhoH), force(RhoH),
+        # force_update(RhoH), 3 MAC velocities, snew(Rho) up; snew(RhoH, valid zones) + EOS mask down
+        h2d = 8 * nb * (C * cells_s + cells_f + 3 * uface + face
+                        + cells_s + 2 * cells_f + 3 * uface + cells_s)
+        d2h = 8 * nb * (C * en ** 3 + face + en ** 3) + nb * en ** 3
+        h2d_mem = 8 * nb * (C * cells_s + C * cells_f + 3 * uface + face
+                            + cells_s + cells_f + 3 * uface + 3 * face)
+        d2h_mem = 8 * nb * (3 * C * face + 3 * C * face + face + 3 * face + 3 * face)
+        upd = en ** 3 * (a.nspec + 2) * nb * world
+        e2e = {"value": upd / te_adv, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "sample": f"{a.e2e_boxes} boxes of {en}^3 per step, pinned host fabs through "
-                         f"mx_density_edge_flux + mx_enthalpy_edge_flux (z-slab pipeline: "
-                         f"H2D / kernel / D2H of consecutive slabs overlap), {nthr} host "
-                         f"thread(s) / stream(s) with boxes in flight"}
+               "sample": f"{nb} boxes of {en}^3 per step, pinned host fabs through "
+                         f"mx_density_advance + mx_enthalpy_advance (what overlay_fused's "
+                         f"DensityAdvance / EnthalpyAdvance call: edge states + fluxes + UpdateScal, "
+                         f"intermediates device resident, new state returned), {nthr} host "
+                         f"thread(s) / stream(s) with boxes in flight",
+               "members": {"value": upd / te_mem, "h2d_bytes_per_step": h2d_mem,
+                           "d2h_bytes_per_step": d2h_mem,
+                           "sample": "same boxes through mx_density_edge_flux + mx_enthalpy_edge_flux "
+                                     "(edge states and fluxes returned to the host, z-slab pipeline)"}}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:

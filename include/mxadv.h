@@ -455,6 +455,46 @@ int mx_update_vel(const MxGeom* geom, const MxFab* uold, const MxFab* unew, cons
                   const MxFab* w0_cart, const MxFab* w0mac, double dt, int do_sponge,
                   int spherical, void* stream);
 
+/* ---- fused advances (the update that follows the fluxes) -------
+ * mx_density_advance = mx_density_edge_flux + the part of DensityAdvance that follows it
+ * (Source/MaestroDensityAdvance.cpp:144-258): rho' -> rho (PutInPertForm, flag false; only for
+ * predict_rhoprime_and_X), X -> rho X (ConvertRhoXToX, flag false), scal_force = 0, UpdateScal
+ * of the species and the density.  Edge states, fluxes, the zero force and the rebuilt old
+ * state live in device workspace and never cross PCIe: a host caller uploads the converted
+ * state (X_k, rho' with ghost cells), the prediction force and the MAC velocities and gets back
+ * the species / density components of `snew` (valid zones) and `etarhoflux`.
+ * species_force_is_zero != 0: only force(Rho) is read (the species components are zero in the
+ * reference, MaestroDensityAdvance.cpp:36-39; saves their upload).  sedge / sflux may be NULL;
+ * if given (device or host fabs, as in mx_density_edge_flux) they receive the edge states and
+ * fluxes as well.  rho0_pert is the base state PutInPertForm adds back (rho0_old); upar as in
+ * mx_update_scal with start_comp = FirstSpec.  3-D; results are bit-identical to the separate
+ * calls. */
+int mx_density_advance(const MxGeom* geom, const MxFab* state, const MxFab* snew,
+                       const MxFab* etarhoflux, const MxFab* umac, const MxFab* force,
+                       int species_force_is_zero, const MxEdgeParams* epar, int rho_bccomp,
+                       const MxBase* rho0_old, const MxBase* rho0_edge_old, const MxFab* r0mac_old,
+                       const MxBase* rho0_new, const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                       const MxBase* rho0_predicted_edge, const MxBase* w0, const MxFluxParams* fpar,
+                       const MxBase* rho0_pert, const MxSphr* sphr, const MxUpdateParams* upar,
+                       const MxFab* sedge /*[3] or NULL*/, const MxFab* sflux /*[3] or NULL*/,
+                       void* stream);
+
+/* mx_enthalpy_advance = mx_enthalpy_edge_flux + (rho h)' -> (rho h) (PutInPertForm with
+ * rhoh0_pert = rhoh0_old, enthalpy_pred_type predict_rhohprime; nothing for predict_rhoh) +
+ * UpdateScal of RhoH with `force_update` (the time-centred force of
+ * Source/MaestroEnthalpyAdvance.cpp:316-336, RhoH component).  `snew` must hold the NEW density
+ * in its Rho component (it decides which zones need the caller's EOS, see mx_update_scal:
+ * eos_mask / n_eos).  Planar base state, 3-D, enthalpy_pred_type 0 or 1.  sedge must be given
+ * when the flux form reads sedge(Rho) (never for types 0 / 1) - pass NULL otherwise. */
+int mx_enthalpy_advance(const MxGeom* geom, const MxFab* state, const MxFab* snew,
+                        const MxFab* umac, const MxFab* force, const MxFab* force_update,
+                        const MxEdgeParams* epar, const MxBase* rho0_old, const MxBase* rho0_edge_old,
+                        const MxBase* rho0_new, const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
+                        const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+                        const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
+                        const MxBase* rhoh0_pert, const MxUpdateParams* upar,
+                        unsigned char* eos_mask, long long* n_eos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

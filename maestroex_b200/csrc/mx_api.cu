@@ -168,6 +168,24 @@ class Session {
         return MX_OK;
     }
 
+    // download only the box [lo, hi] of components [c0, c0+nc) at finish(): for outputs that are
+    // written on the valid zones only, so that the host fab's ghost zones neither have to be
+    // uploaded first nor travel back (one strided 3-D copy per component)
+    int download_box(const MxFab* f, const DFab& d, int c0, int nc, const int lo[3], const int hi[3]) {
+        if (is_device_ptr(f->p) || nc <= 0) return MX_OK;
+        Back3 b;
+        b.host = f->p;
+        b.g = d;
+        b.c0 = c0;
+        b.nc = nc;
+        for (int q = 0; q < 3; ++q) {
+            b.lo[q] = lo[q];
+            b.hi[q] = hi[q];
+        }
+        backs3_.push_back(b);
+        return MX_OK;
+    }
+
     // 1-D base-state array at level `lev` -> device pointer + stride
     int base(const MxBase* b, int lev, const double** p, int* stride) {
         *p = nullptr;
@@ -200,6 +218,20 @@ class Session {
         }
         for (auto& b : backs_) {
             CUDA_OK(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st_));
+        }
+        for (auto& b : backs3_) {
+            const size_t off = (size_t)(b.lo[0] - b.g.lo[0]) + (size_t)(b.lo[1] - b.g.lo[1]) * b.g.sy +
+                               (size_t)(b.lo[2] - b.g.lo[2]) * b.g.sz;
+            for (int c = b.c0; c < b.c0 + b.nc; ++c) {
+                cudaMemcpy3DParms p3 = {};
+                const size_t pitch = sizeof(double) * (size_t)b.g.n[0];
+                p3.srcPtr = make_cudaPitchedPtr(b.g.p + (size_t)c * b.g.sn + off, pitch, b.g.n[0], b.g.n[1]);
+                p3.dstPtr = make_cudaPitchedPtr(b.host + (size_t)c * b.g.sn + off, pitch, b.g.n[0], b.g.n[1]);
+                p3.extent = make_cudaExtent(sizeof(double) * (size_t)(b.hi[0] - b.lo[0] + 1),
+                                            (size_t)(b.hi[1] - b.lo[1] + 1), (size_t)(b.hi[2] - b.lo[2] + 1));
+                p3.kind = cudaMemcpyDeviceToHost;
+                CUDA_OK(cudaMemcpy3DAsync(&p3, st_));
+            }
         }
         if (any_host_) CUDA_OK(cudaStreamSynchronize(st_));
         return MX_OK;
@@ -371,6 +403,12 @@ class Session {
     cudaStream_t st_;
     std::vector<void*> owned_;
     std::vector<Back> backs_;
+    struct Back3 {
+        double* host;
+        DFab g;
+        int c0, nc, lo[3], hi[3];
+    };
+    std::vector<Back3> backs3_;
     bool any_host_ = false;
     size_t h2d_ = 0;
 };
@@ -1537,6 +1575,187 @@ int mx_update_vel(const MxGeom* geom, const MxFab* uold, const MxFab* unew, cons
         MX_TRY(S.fab(w0_cart, &w0c, last, 1, true, false));
     }
     cart_update_vel(make_kgeom(geom), uo, un, um, ue, fo, sp, w0c, wm, dt, do_sponge, spherical, S.stream());
+    return S.finish();
+}
+
+}  // extern "C"
+
+// ==== fused advances: device-resident composition of the entry points above =================
+namespace {
+// device fab over box [lo, hi] with ncomp components out of the session's workspace
+int ws_fab(Session& S, const int lo[3], const int hi[3], int ncomp, MxFab* out, bool zero) {
+    for (int d = 0; d < 3; ++d) {
+        out->lo[d] = lo[d];
+        out->hi[d] = hi[d];
+    }
+    out->ncomp = ncomp;
+    size_t n = (size_t)ncomp;
+    for (int d = 0; d < 3; ++d) n *= (size_t)(hi[d] - lo[d] + 1);
+    void* p = nullptr;
+    CUDA_OK(S.alloc(&p, n * sizeof(double)));
+    if (zero) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), S.stream()));
+    out->p = static_cast<double*>(p);
+    return MX_OK;
+}
+void valid_box3(const MxGeom* g, int nodal_dir, int lo[3], int hi[3]) {
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = d < g->dim ? g->valid_lo[d] : 0;
+        hi[d] = d < g->dim ? g->valid_hi[d] + (d == nodal_dir ? 1 : 0) : 0;
+    }
+}
+// device view of a caller fab as an MxFab (uploads comps [c0, c0+nc) of a host fab)
+int dev_view(Session& S, const MxFab* f, int c0, int nc, bool in, bool out, MxFab* v, DFab* d) {
+    MX_TRY(S.fab(f, d, c0, nc, in, out));
+    *v = *f;
+    v->p = d->p;
+    return MX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mx_density_advance(const MxGeom* geom, const MxFab* state, const MxFab* snew,
+                       const MxFab* etarhoflux, const MxFab* umac, const MxFab* force,
+                       int species_force_is_zero, const MxEdgeParams* epar, int rho_bccomp,
+                       const MxBase* rho0_old, const MxBase* rho0_edge_old, const MxFab* r0mac_old,
+                       const MxBase* rho0_new, const MxBase* rho0_edge_new, const MxFab* r0mac_new,
+                       const MxBase* rho0_predicted_edge, const MxBase* w0, const MxFluxParams* fpar,
+                       const MxBase* rho0_pert, const MxSphr* sphr, const MxUpdateParams* upar,
+                       const MxFab* sedge, const MxFab* sflux, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!state || !snew || !umac || !force || !epar || !fpar || !upar)
+        return fail(MX_ERR_INVALID, "null argument");
+    if (geom->dim != 3) return fail(MX_ERR_UNSUPPORTED, "mx_density_advance is 3-D only");
+    if (upar->start_comp != upar->first_spec || upar->first_spec != fpar->first_spec ||
+        upar->num_spec != fpar->num_spec || upar->rho_comp != fpar->rho_comp)
+        return fail(MX_ERR_INVALID, "update parameters do not describe the species update of this pass");
+    const bool pert = fpar->species_pred_type == MX_PRED_RHOPRIME_AND_X;
+    if (pert && (!rho0_pert || !rho0_pert->p)) return fail(MX_ERR_INVALID, "rho0_pert is required");
+    if (snew->ncomp != state->ncomp) return fail(MX_ERR_INVALID, "snew / state component counts differ");
+    MX_TRY(check_cover(geom, snew, 0, -1, "snew"));
+    MX_TRY(require_device());
+    Session S(stream);
+    const int rho = fpar->rho_comp, c0 = fpar->first_spec, nc = fpar->num_spec;
+    // 1. device views of the inputs (host fabs are uploaded once, here)
+    MxFab v_state, v_force, v_umac[3], v_snew, v_eta;
+    DFab d_state, d_force, d_umac[3], d_snew, d_eta;
+    MX_TRY(dev_view(S, state, c0, nc, true, false, &v_state, &d_state));
+    MX_TRY(S.upload(state, d_state, rho, 1));
+    if (species_force_is_zero && !is_device_ptr(force->p)) {
+        MX_TRY(dev_view(S, force, rho, 1, true, false, &v_force, &d_force));
+        CUDA_OK(cudaMemsetAsync(d_force.comp(c0), 0, sizeof(double) * (size_t)d_force.sn * nc, S.stream()));
+    } else {
+        MX_TRY(dev_view(S, force, c0, nc, true, false, &v_force, &d_force));
+        MX_TRY(S.upload(force, d_force, rho, 1));
+    }
+    for (int d = 0; d < 3; ++d) MX_TRY(dev_view(S, &umac[d], 0, 1, true, false, &v_umac[d], &d_umac[d]));
+    // snew: the species / density components are fully overwritten on the valid zones and
+    // nothing else is touched: no upload, and only the valid box travels back
+    MX_TRY(dev_view(S, snew, c0, nc, false, false, &v_snew, &d_snew));
+    {
+        int vlo[3], vhi[3];
+        valid_box3(geom, -1, vlo, vhi);
+        MX_TRY(S.download_box(snew, d_snew, c0, nc, vlo, vhi));
+        MX_TRY(S.download_box(snew, d_snew, rho, 1, vlo, vhi));
+    }
+    const bool do_eta = !fpar->spherical && fpar->evolve_base_state && !fpar->use_exact_base_state;
+    if (etarhoflux) MX_TRY(dev_view(S, etarhoflux, 0, 1, true, do_eta, &v_eta, &d_eta));
+    // 2. edge states + fluxes into workspace (or the caller's fabs)
+    MxFab w_sedge[3], w_sflux[3];
+    DFab dd;
+    for (int d = 0; d < 3; ++d) {
+        int lo[3], hi[3];
+        valid_box3(geom, d, lo, hi);
+        if (sedge) {
+            MX_TRY(dev_view(S, &sedge[d], c0, nc, false, true, &w_sedge[d], &dd));
+            MX_TRY(S.download_later(&sedge[d], dd, rho, 1));
+        } else {
+            MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_sedge[d], false));
+        }
+        if (sflux) {
+            MX_TRY(dev_view(S, &sflux[d], c0, nc, false, true, &w_sflux[d], &dd));
+            MX_TRY(S.download_later(&sflux[d], dd, rho, 1));
+        } else {
+            MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_sflux[d], false));
+        }
+    }
+    MX_TRY(mx_density_edge_flux(geom, &v_state, w_sedge, w_sflux, etarhoflux ? &v_eta : nullptr, v_umac,
+                                &v_force, epar, rho_bccomp, rho0_old, rho0_edge_old, r0mac_old, rho0_new,
+                                rho0_edge_new, r0mac_new, rho0_predicted_edge, w0, fpar, S.stream()));
+    // 3. the old state as UpdateScal sees it: rho' + rho0 -> rho, X rho -> rho X (valid zones)
+    MxFab w_sold, w_zero;
+    int lo[3], hi[3];
+    valid_box3(geom, -1, lo, hi);
+    MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_sold, false));
+    MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_zero, true));  // scal_force.setVal(0), :241-243
+    const KGeom kg = make_kgeom(geom);
+    const DFab d_sold = make_dfab(&w_sold, w_sold.p);
+    cart_copy_valid(kg, d_state, d_sold, c0, nc, S.stream());
+    cart_copy_valid(kg, d_state, d_sold, rho, 1, S.stream());
+    if (pert) MX_TRY(mx_put_in_pert_form(geom, &w_sold, rho0_pert, fpar->lev, rho, 0, sphr, S.stream()));
+    MX_TRY(mx_convert_by_rho(geom, &w_sold, rho, c0, nc, 0, S.stream()));
+    // 4. UpdateScal (species + density)
+    MX_TRY(mx_update_scal(geom, &w_sold, &v_snew, w_sflux, &w_zero, upar, nullptr, nullptr, S.stream()));
+    return S.finish();
+}
+
+int mx_enthalpy_advance(const MxGeom* geom, const MxFab* state, const MxFab* snew, const MxFab* umac,
+                        const MxFab* force, const MxFab* force_update, const MxEdgeParams* epar,
+                        const MxBase* rho0_old, const MxBase* rho0_edge_old, const MxBase* rho0_new,
+                        const MxBase* rho0_edge_new, const MxBase* rhoh0_old,
+                        const MxBase* rhoh0_edge_old, const MxBase* rhoh0_new,
+                        const MxBase* rhoh0_edge_new, const MxFluxParams* fpar,
+                        const MxBase* rhoh0_pert, const MxUpdateParams* upar, unsigned char* eos_mask,
+                        long long* n_eos, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!state || !snew || !umac || !force || !force_update || !epar || !fpar || !upar)
+        return fail(MX_ERR_INVALID, "null argument");
+    if (geom->dim != 3) return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_advance is 3-D only");
+    if (fpar->spherical) return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_advance: planar base state only");
+    if (fpar->enthalpy_pred_type != MX_PRED_RHOH && fpar->enthalpy_pred_type != MX_PRED_RHOHPRIME)
+        return fail(MX_ERR_UNSUPPORTED, "mx_enthalpy_advance: enthalpy_pred_type %d (only predict_rhoh / "
+                    "predict_rhohprime)", fpar->enthalpy_pred_type);
+    if (upar->start_comp != upar->rhoh_comp || upar->rhoh_comp != fpar->rhoh_comp)
+        return fail(MX_ERR_INVALID, "update parameters do not describe the enthalpy update of this pass");
+    const bool pert = fpar->enthalpy_pred_type == MX_PRED_RHOHPRIME;
+    if (pert && (!rhoh0_pert || !rhoh0_pert->p)) return fail(MX_ERR_INVALID, "rhoh0_pert is required");
+    if (snew->ncomp != state->ncomp) return fail(MX_ERR_INVALID, "snew / state component counts differ");
+    MX_TRY(check_cover(geom, snew, 0, -1, "snew"));
+    MX_TRY(require_device());
+    Session S(stream);
+    const int rhoh = fpar->rhoh_comp, rho = fpar->rho_comp;
+    MxFab v_state, v_force, v_fupd, v_umac[3], v_snew;
+    DFab d_state, d_force, d_fupd, d_umac[3], d_snew;
+    MX_TRY(dev_view(S, state, rhoh, 1, true, false, &v_state, &d_state));
+    MX_TRY(dev_view(S, force, rhoh, 1, true, false, &v_force, &d_force));
+    MX_TRY(dev_view(S, force_update, rhoh, 1, true, false, &v_fupd, &d_fupd));
+    for (int d = 0; d < 3; ++d) MX_TRY(dev_view(S, &umac[d], 0, 1, true, false, &v_umac[d], &d_umac[d]));
+    MX_TRY(dev_view(S, snew, rhoh, 1, false, false, &v_snew, &d_snew));
+    {
+        int vlo[3], vhi[3];
+        valid_box3(geom, -1, vlo, vhi);
+        MX_TRY(S.download_box(snew, d_snew, rhoh, 1, vlo, vhi));
+    }
+    MX_TRY(S.upload(snew, d_snew, rho, 1));  // the new density decides the EOS zones
+    MxFab w_sedge[3], w_sflux[3];
+    for (int d = 0; d < 3; ++d) {
+        int lo[3], hi[3];
+        valid_box3(geom, d, lo, hi);
+        MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_sedge[d], false));
+        MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_sflux[d], false));
+    }
+    MX_TRY(mx_enthalpy_edge_flux(geom, &v_state, w_sedge, w_sflux, v_umac, &v_force, epar, rho0_old,
+                                 rho0_edge_old, rho0_new, rho0_edge_new, rhoh0_old, rhoh0_edge_old,
+                                 rhoh0_new, rhoh0_edge_new, fpar, S.stream()));
+    MxFab w_sold;
+    int lo[3], hi[3];
+    valid_box3(geom, -1, lo, hi);
+    MX_TRY(ws_fab(S, lo, hi, state->ncomp, &w_sold, false));
+    const KGeom kg = make_kgeom(geom);
+    cart_copy_valid(kg, d_state, make_dfab(&w_sold, w_sold.p), rhoh, 1, S.stream());
+    if (pert) MX_TRY(mx_put_in_pert_form(geom, &w_sold, rhoh0_pert, fpar->lev, rhoh, 0, nullptr, S.stream()));
+    // eos_mask / n_eos: device or host, exactly as mx_update_scal takes them
+    MX_TRY(mx_update_scal(geom, &w_sold, &v_snew, w_sflux, &v_fupd, upar, eos_mask, n_eos, S.stream()));
     return S.finish();
 }
 

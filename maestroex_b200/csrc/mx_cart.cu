@@ -141,6 +141,13 @@ void cart_convert_by_rho(const KGeom& g, const DFab& s, int rho, int c0, int nc,
     });
 }
 
+// copy components [c0, c0+nc) of the valid box (MultiFab::Copy with 0 ghost cells)
+void cart_copy_valid(const KGeom& g, const DFab& src, const DFab& dst, int c0, int nc, cudaStream_t st) {
+    for_box(valid_box(g), st, [=] __device__(int i, int j, int k) {
+        for (int n = c0; n < c0 + nc; ++n) at(dst, i, j, k, n) = at(src, i, j, k, n);
+    });
+}
+
 // ---- Put1dArrayOnCart / PutInPertForm ------------------------------------------------------
 // mode 0: store; 1: scal -= value; 2: scal += value (PutInPertForm, component `comp`)
 void cart_put_1d(const KGeom& g, const double* s0, int st0, const DFab& out, int edge, int vec,

@@ -16,6 +16,7 @@ struct KSphr {
 
 void cart_convert_by_rho(const KGeom& g, const DFab& s, int rho, int c0, int nc, int flag,
                          cudaStream_t st);
+void cart_copy_valid(const KGeom& g, const DFab& src, const DFab& dst, int c0, int nc, cudaStream_t st);
 void cart_put_1d(const KGeom& g, const double* s0, int st0, const DFab& out, int edge, int vec,
                  int mode, int comp, const KSphr& S, cudaStream_t st);
 void cart_modify_scal_force(const KGeom& g, const DFab& force, const DFab& state, const DFab* umac,

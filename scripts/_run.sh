@@ -1,19 +1,14 @@
-mkdir -p gpurun_out/n8
-timeout -k 10 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -k "4-1 or 8-0" 2>&1 | tail -4
-run() {  # run <label> <bench args...>
-  local label=$1; shift
-  timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu --no-e2e "$@" > gpurun_out/n8/bench_n8_$label.json 2> gpurun_out/n8/bench_n8_$label.err
-  python - gpurun_out/n8/bench_n8_$label.json $label <<'PY'
-import json,sys
+mkdir -p gpurun_out/adv
+timeout -k 10 900 python -m pytest tests/test_gpu_advance.py tests/test_w0.py -x -q -m gpu 2>&1 | tail -12
+timeout -k 10 900 python bench.py --size 256 --steps 5 --warmup 3 --no-cpu > gpurun_out/adv/bench_256_e2e.json 2> gpurun_out/adv/bench_256_e2e.err; python - <<'PY'
+import json
 try:
-    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[2], "value %.4g ms/step %.2f"%(d["value"], d["ms_per_step"]), d["config"].get("halo_exchange"))
-except Exception as e: print(sys.argv[2], "FAILED", e)
+    d=json.loads(open('gpurun_out/adv/bench_256_e2e.json').read().strip().splitlines()[-1]); e=d["e2e"]; print("value %.4g e2e %.4g members %.4g"%(d["value"], e["value"], e["members"]["value"]), e["h2d_bytes_per_step"], e["d2h_bytes_per_step"])
+except Exception as ex: print("FAILED", ex); print(open('gpurun_out/adv/bench_256_e2e.err').read()[-1500:])
 PY
-}
-run 512_ppm1_nspec13_nccl
-run 512_ppm1_nspec13_p2p --halo p2p
-run 512_ppm1_nspec13_nohalo --no-halo
-run 512_sph_ppm1_nspec13 --spherical --bc outflow
-run 512_ppm0_nspec3 --ppm 0 --nspec 3
-run 512_ppm2_nspec13 --ppm 2
-run 448_ppm1_nspec21 --nspec 21 --size 448
+timeout -k 10 900 python bench.py --size 256 --steps 5 --warmup 3 --no-cpu --e2e-threads 4 > gpurun_out/adv/bench_256_e2e_t4.json 2> gpurun_out/adv/bench_256_e2e_t4.err; python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/adv/bench_256_e2e_t4.json').read().strip().splitlines()[-1]); e=d["e2e"]; print("4 threads: e2e %.4g members %.4g"%(e["value"], e["members"]["value"]))
+except Exception as ex: print("FAILED", ex)
+PY
