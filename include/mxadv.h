@@ -417,11 +417,15 @@ int mx_put_in_pert_form(const MxGeom* geom, const MxFab* scal, const MxBase* s0,
  * at the top domain face (bcf_hi: MX_BC_FOEXTRAP / MX_BC_REFLECT_EVEN -> s0_edge(domhi),
  * MX_BC_INT_DIR (periodic) -> s0_edge(domlo)).  Spherical (3-D): s0_cart with 1 ghost,
  * div(w0) evaluated from the 1-D w0 (nr_fine+1) as the reference does (divw0 table, then
- * Put1dArrayOnCart(divw0, ., false, false)); w0_cart and s0_edge are not read. */
+ * Put1dArrayOnCart(divw0, ., false, false)); w0_cart and s0_edge are not read.
+ * s0_edge_cart (optional, planar): the 1-ghost MultiFab itself, as the reference builds it with
+ * Put1dArrayOnCart + FillPatch; when given it is read instead of s0_edge / bcf_hi (what an AMR
+ * caller passes: at coarse-fine boundaries FillPatch interpolates from the coarser level). */
 int mx_modify_scal_force(const MxGeom* geom, const MxFab* scal_force, const MxFab* state,
                          const MxFab* umac /*[dim]*/, const MxBase* s0_edge, int lev,
                          const MxFab* s0_cart, const MxFab* w0_cart, const double* w0,
-                         int comp, int fullform, int bcf_hi, const MxSphr* sphr, void* stream);
+                         int comp, int fullform, int bcf_hi, const MxFab* s0_edge_cart,
+                         const MxSphr* sphr, void* stream);
 
 /* Maestro::Addw0 (Source/MaestroFill3dData.cpp:357-461), the add itself: planar
  * uedge[dim-1](i,j,r) += mult * w0(lev,r) on the nodal valid box grown by one in the transverse
@@ -442,9 +446,10 @@ int mx_make_w0mac(const MxGeom* geom, const MxFab* w0mac /*[3]*/, const MxFab* w
  * averages the cell-centred mapping of s0 (Put1dArrayOnCart + FillPatch with bcs_f in the
  * reference: cells outside the domain take the first-order extrapolation, i.e. the value of the
  * nearest cell inside; evaluated on the fly here, no s0_cart temporary); types 2 and 3
- * interpolate to the face centres directly. */
+ * interpolate to the face centres directly.  s0_cart (optional, type 1): the 2-ghost MultiFab
+ * itself after the caller's FillPatch, read instead of the on-the-fly mapping (AMR callers). */
 int mx_make_s0mac(const MxGeom* geom, const MxBase* s0, const MxFab* s0mac /*[3]*/,
-                  const MxSphr* sphr, void* stream);
+                  const MxFab* s0_cart, const MxSphr* sphr, void* stream);
 
 /* Maestro::UpdateVel (Source/MaestroAdvection.cpp:299-526), zone loop on the valid box:
  * unew = uold - dt (Utilde . grad) Utilde + dt force - dt (w0 . grad) Utilde, times the sponge.

@@ -186,12 +186,12 @@ class Calls:
     # -- Maestro::ModifyScalForce (Source/MaestroForce.cpp:261-467) -----------------------
     def modify_scal_force(self, geom: Geom, scal_force: Fab, state: Fab, umac, s0_edge: Base,
                           lev: int, s0_cart: Fab, w0_cart: Fab, w0, comp: int, fullform: int,
-                          bcf_hi: int, sphr: Sphr = None, stream: int = 0):
+                          bcf_hi: int, sphr: Sphr = None, stream: int = 0, s0_edge_cart: Fab = None):
         g, f, st, s0c = geom.c(), scal_force.c(), state.c(), s0_cart.c()
         rc = self._fn("modify_scal_force")(
             C.byref(g), C.byref(f), C.byref(st), self._faces(umac), self._base(s0_edge), lev,
             C.byref(s0c), self._fab(w0_cart), self._vp(w0), comp, fullform, bcf_hi,
-            self._sphr(sphr), *self._tail(stream))
+            self._fab(s0_edge_cart), self._sphr(sphr), *self._tail(stream))
         self._check(rc, "modify_scal_force")
 
     # -- Maestro::Addw0 (Source/MaestroFill3dData.cpp:357-461) ----------------------------
@@ -209,9 +209,9 @@ class Calls:
                                     self._vp(w0), self._sphr(sphr), *self._tail(stream))
         self._check(rc, "make_w0mac")
 
-    def make_s0mac(self, geom: Geom, s0: Base, s0mac, sphr: Sphr, stream: int = 0):
+    def make_s0mac(self, geom: Geom, s0: Base, s0mac, sphr: Sphr, stream: int = 0, s0_cart: Fab = None):
         g = geom.c()
-        rc = self._fn("make_s0mac")(C.byref(g), self._base(s0), self._faces(s0mac),
+        rc = self._fn("make_s0mac")(C.byref(g), self._base(s0), self._faces(s0mac), self._fab(s0_cart),
                                     self._sphr(sphr), *self._tail(stream))
         self._check(rc, "make_s0mac")
 

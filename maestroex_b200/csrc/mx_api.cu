@@ -1378,7 +1378,7 @@ int mx_put_in_pert_form(const MxGeom* geom, const MxFab* scal, const MxBase* s0,
 int mx_modify_scal_force(const MxGeom* geom, const MxFab* scal_force, const MxFab* state,
                          const MxFab* umac, const MxBase* s0_edge, int lev, const MxFab* s0_cart,
                          const MxFab* w0_cart, const double* w0, int comp, int fullform, int bcf_hi,
-                         const MxSphr* sphr, void* stream) {
+                         const MxFab* s0_edge_cart, const MxSphr* sphr, void* stream) {
     MX_TRY(check_geom(geom));
     if (!scal_force || !state || !umac || !s0_cart) return fail(MX_ERR_INVALID, "null argument");
     const bool sph = sphr && sphr->spherical;
@@ -1390,13 +1390,21 @@ int mx_modify_scal_force(const MxGeom* geom, const MxFab* scal_force, const MxFa
         MX_TRY(check_type(sphr->s0_interp_type, 3, "s0_interp_type"));
         MX_TRY(check_cover(geom, s0_cart, fullform == 1 ? 0 : 1, -1, "s0_cart"));
     } else {
-        if (!w0_cart || !s0_edge || !s0_edge->p) return fail(MX_ERR_INVALID, "planar: w0_cart and s0_edge are required");
+        if (!w0_cart) return fail(MX_ERR_INVALID, "planar: w0_cart is required");
         if (w0_cart->ncomp < geom->dim) return fail(MX_ERR_INVALID, "w0_cart needs dim components");
-        if (bcf_hi != MX_BC_INT_DIR && bcf_hi != MX_BC_FOEXTRAP && bcf_hi != MX_BC_REFLECT_EVEN)
-            return fail(MX_ERR_INVALID, "bcf_hi must be a bcs_f code (int_dir, foextrap, reflect_even)");
         const int last = geom->dim - 1;
-        if (geom->valid_lo[last] < 0 || geom->valid_hi[last] + 1 >= s0_edge->len)
-            return fail(MX_ERR_INVALID, "s0_edge does not cover the box");
+        if (s0_edge_cart) {
+            for (int d = 0; d < geom->dim; ++d)
+                if (s0_edge_cart->lo[d] > geom->valid_lo[d] ||
+                    s0_edge_cart->hi[d] < geom->valid_hi[d] + (d == last ? 1 : 0))
+                    return fail(MX_ERR_INVALID, "s0_edge_cart needs one ghost cell in the last direction");
+        } else {
+            if (!s0_edge || !s0_edge->p) return fail(MX_ERR_INVALID, "planar: s0_edge (or s0_edge_cart) is required");
+            if (bcf_hi != MX_BC_INT_DIR && bcf_hi != MX_BC_FOEXTRAP && bcf_hi != MX_BC_REFLECT_EVEN)
+                return fail(MX_ERR_INVALID, "bcf_hi must be a bcs_f code (int_dir, foextrap, reflect_even)");
+            if (geom->valid_lo[last] < 0 || geom->valid_hi[last] + 1 >= s0_edge->len)
+                return fail(MX_ERR_INVALID, "s0_edge does not cover the box");
+        }
         MX_TRY(check_cover(geom, s0_cart, 0, -1, "s0_cart"));
         for (int d = 0; d < geom->dim; ++d) {  // one ghost cell above in the last direction
             const int ng = d == last ? 1 : 0;
@@ -1432,10 +1440,12 @@ int mx_modify_scal_force(const MxGeom* geom, const MxFab* scal_force, const MxFa
         ws = static_cast<double*>(q);
     } else {
         MX_TRY(S.fab(w0_cart, &w0c, geom->dim - 1, 1, true, false));
-        MX_TRY(S.base(s0_edge, lev, &pe, &ste));
+        if (!s0_edge_cart) MX_TRY(S.base(s0_edge, lev, &pe, &ste));
     }
+    DFab ecd;
+    if (!sph && s0_edge_cart) MX_TRY(S.fab(s0_edge_cart, &ecd, 0, 1, true, false));
     cart_modify_scal_force(make_kgeom(geom), f, stt, um, pe, ste, s0c, w0c, dw0, ws, comp, fullform, bcf_hi,
-                           ks, S.stream());
+                           (!sph && s0_edge_cart) ? &ecd : nullptr, ks, S.stream());
     return S.finish();
 }
 
@@ -1506,13 +1516,14 @@ int mx_make_w0mac(const MxGeom* geom, const MxFab* w0mac, const MxFab* w0_cart, 
     return S.finish();
 }
 
-int mx_make_s0mac(const MxGeom* geom, const MxBase* s0, const MxFab* s0mac, const MxSphr* sphr,
-                  void* stream) {
+int mx_make_s0mac(const MxGeom* geom, const MxBase* s0, const MxFab* s0mac, const MxFab* s0_cart,
+                  const MxSphr* sphr, void* stream) {
     MX_TRY(check_geom(geom));
     if (!s0mac || !sphr || !s0 || !s0->p) return fail(MX_ERR_INVALID, "null argument");
     if (!sphr->spherical || geom->dim != 3) return fail(MX_ERR_INVALID, "Error: only call MakeS0mac for spherical");
     MX_TRY(check_type(sphr->s0mac_interp_type, 3, "s0mac_interp_type"));
-    if (sphr->s0mac_interp_type == 1) MX_TRY(check_type(sphr->s0_interp_type, 3, "s0_interp_type"));
+    if (sphr->s0mac_interp_type == 1 && !s0_cart) MX_TRY(check_type(sphr->s0_interp_type, 3, "s0_interp_type"));
+    if (sphr->s0mac_interp_type == 1 && s0_cart) MX_TRY(check_cover(geom, s0_cart, 2, -1, "s0_cart"));
     for (int d = 0; d < 3; ++d) MX_TRY(check_cover(geom, &s0mac[d], 1, d, "s0mac"));
     MX_TRY(require_device());
     Session S(stream);
@@ -1523,7 +1534,10 @@ int mx_make_s0mac(const MxGeom* geom, const MxBase* s0, const MxFab* s0mac, cons
     const double* p;
     int st;
     MX_TRY(S.base(s0, 0, &p, &st));
-    cart_make_s0mac(make_kgeom(geom), p, st, sm, ks, S.stream());
+    DFab s0c;
+    const bool use_cart = sphr->s0mac_interp_type == 1 && s0_cart;
+    if (use_cart) MX_TRY(S.fab(s0_cart, &s0c, 0, 1, true, false));
+    cart_make_s0mac(make_kgeom(geom), p, st, sm, use_cart ? &s0c : nullptr, ks, S.stream());
     return S.finish();
 }
 

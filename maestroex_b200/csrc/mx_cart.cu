@@ -59,11 +59,20 @@ __device__ __forceinline__ double& at(const DFab& f, int i, int j, int k, int n 
     return f.p[f.off(i, j, k) + (long)n * f.sn];
 }
 
-// Source/MaestroFill3dData.cpp:339-355 (limit = false at every call site on this path)
+// std::min / std::max semantics (amrex::min/max)
+__device__ __forceinline__ double dmin_(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double dmax_(double a, double b) { return (a < b) ? b : a; }
+
+// QuadInterp, Source/MaestroFill3dData.cpp:339-355, with its default limit = true
+// (Source/Maestro.H:65-68; every call site on this path leaves the argument out)
 __device__ __forceinline__ double quad_interp(double x, double x0, double x1, double x2, double y0,
                                               double y1, double y2) {
-    return y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
-           ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+    double y = y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
+               ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+    const double hi = dmax_(y0, dmax_(y1, y2)), lo = dmin_(y0, dmin_(y1, y2));
+    if (y > hi) y = hi;
+    if (y < lo) y = lo;
+    return y;
 }
 
 // edge-centred 1-D array -> value at `radius` (MaestroFill3dData.cpp:218-250, :534-575)
@@ -200,7 +209,7 @@ __global__ void k_divw0(const double* w0, const double* rcc, const double* redge
 void cart_modify_scal_force(const KGeom& g, const DFab& force, const DFab& state, const DFab* umac,
                             const double* s0e, int st_e, const DFab& s0c, const DFab& w0c,
                             const double* w0, double* divw0_ws, int comp, int fullform, int bcf_hi,
-                            const KSphr& S, cudaStream_t st) {
+                            const DFab* s0ec, const KSphr& S, cudaStream_t st) {
     DX3 dx = {{g.dx[0], g.dx[1], g.dx[2]}};
     const int dim = g.dim;
     const DFab um = umac[0], vm = umac[1], wm = umac[dim == 3 ? 2 : 1];
@@ -243,11 +252,21 @@ void cart_modify_scal_force(const KGeom& g, const DFab& force, const DFab& state
     // top domain face (MaestroForce.cpp:275-277 with Put1dArrayOnCart's FillPatch)
     const int last = dim - 1;
     const int dhi = g.dhi[last], dlo = g.dlo[last];
+    const bool have_ec = s0ec != nullptr;
+    DFab ec;
+    if (have_ec) ec = *s0ec;
     for_box(valid_box(g), st, [=] __device__(int i, int j, int k) {
         const int r = dim == 2 ? j : k;
-        int rp = r + 1;
-        if (r == dhi) rp = (bcf_hi == MX_BC_INT_DIR) ? dlo : dhi;
-        const double e_lo = s0e[r * st_e], e_hi = s0e[rp * st_e];
+        double e_lo, e_hi;
+        if (have_ec) {
+            e_lo = at(ec, i, j, k);
+            e_hi = dim == 2 ? at(ec, i, j + 1, k) : at(ec, i, j, k + 1);
+        } else {
+            int rp = r + 1;
+            if (r == dhi) rp = (bcf_hi == MX_BC_INT_DIR) ? dlo : dhi;
+            e_lo = s0e[r * st_e];
+            e_hi = s0e[rp * st_e];
+        }
         const double sc = at(state, i, j, k, comp);
         const double s0 = at(s0c, i, j, k);
         double& f = at(force, i, j, k, comp);
@@ -350,8 +369,8 @@ void cart_make_w0mac(const KGeom& g, const DFab* w0mac, const DFab& w0c, const d
 }
 
 // ---- MakeS0mac -----------------------------------------------------------------------------
-void cart_make_s0mac(const KGeom& g, const double* s0, int st0, const DFab* s0mac, const KSphr& S,
-                     cudaStream_t st) {
+void cart_make_s0mac(const KGeom& g, const double* s0, int st0, const DFab* s0mac, const DFab* s0c,
+                     const KSphr& S, cudaStream_t st) {
     DX3 dx = {{g.dx[0], g.dx[1], g.dx[2]}};
     const int type = S.s0mt;
     const int dlo0 = g.dlo[0], dlo1 = g.dlo[1], dlo2 = g.dlo[2];
@@ -359,7 +378,12 @@ void cart_make_s0mac(const KGeom& g, const double* s0, int st0, const DFab* s0ma
     for (int d = 0; d < 3; ++d) {
         const DFab m = s0mac[d];
         const Box3 b = nodal_box(g, d, 1);
-        if (type == 1) {
+        if (type == 1 && s0c != nullptr) {
+            const DFab c = *s0c;
+            for_box(b, st, [=] __device__(int i, int j, int k) {
+                at(m, i, j, k) = 0.5 * (at(c, i - (d == 0), j - (d == 1), k - (d == 2)) + at(c, i, j, k));
+            });
+        } else if (type == 1) {
             for_box(b, st, [=] __device__(int i, int j, int k) {
                 // s0_cart = Put1dArrayOnCart(s0, ., false, false, bcs_f) with 2 ghost cells:
                 // outside the domain the first-order extrapolation = nearest cell inside

@@ -22,13 +22,13 @@ void cart_put_1d(const KGeom& g, const double* s0, int st0, const DFab& out, int
 void cart_modify_scal_force(const KGeom& g, const DFab& force, const DFab& state, const DFab* umac,
                             const double* s0e, int st_e, const DFab& s0c, const DFab& w0c,
                             const double* w0, double* divw0_ws, int comp, int fullform, int bcf_hi,
-                            const KSphr& S, cudaStream_t st);
+                            const DFab* s0ec, const KSphr& S, cudaStream_t st);
 void cart_addw0(const KGeom& g, const DFab* ue, const DFab* w0mac, const double* w0, int st_w,
                 double mult, int spherical, cudaStream_t st);
 void cart_make_w0mac(const KGeom& g, const DFab* w0mac, const DFab& w0c, const double* w0,
                      const KSphr& S, cudaStream_t st);
-void cart_make_s0mac(const KGeom& g, const double* s0, int st0, const DFab* s0mac, const KSphr& S,
-                     cudaStream_t st);
+void cart_make_s0mac(const KGeom& g, const double* s0, int st0, const DFab* s0mac, const DFab* s0c,
+                     const KSphr& S, cudaStream_t st);
 void cart_update_vel(const KGeom& g, const DFab& uold, const DFab& unew, const DFab* umac,
                      const DFab* uedge, const DFab& force, const DFab& sponge, const DFab& w0c,
                      const DFab* w0mac, double dt, int do_sponge, int spherical, cudaStream_t st);

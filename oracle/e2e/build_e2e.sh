@@ -92,6 +92,38 @@ EOF2
     cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d$SUF.fx.ex"
 fi
 
+# 2c. the companion overlay on top: ConvertRhoXToX / ConvertRhoHToH /
+#     PutInPertForm, ModifyScalForce, Put1dArrayOnCart / Addw0 / MakeW0mac / MakeS0mac, UpdateVel on
+#     libmxadv.so.  They share translation units with members that stay the reference's, so those
+#     reference files are compiled with the overlaid members renamed.
+if [ "$DIM" = 3 ]; then BASE=fx; else BASE=mx; fi
+rm -rf "$WORK/${TAGP}cx$DIM"
+cp -r "$WORK/${TAGP}${BASE}$DIM" "$WORK/${TAGP}cx$DIM"
+cd "$WORK/${TAGP}cx$DIM"
+rm -f Maestro${DIM}d.gnu.OMP.ex
+for f in MaestroConvert MaestroForce MaestroFill3dData MaestroAdvection; do
+    find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
+done
+python3 - "$REPO" <<'EOF3'
+import sys
+repo = sys.argv[1]
+mk = open("GNUmakefile").read()
+key = "LIBRARIES         += -lmxadv"
+add = """Bpack   += $(MXADV_HOME)/maestroex_b200/overlay_companions/Make.package
+Blocs   += $(MXADV_HOME)/maestroex_b200/overlay_companions
+"""
+tail = """
+$(objEXETempDir)/MaestroAdvection.o: CPPFLAGS += -DUpdateVel=UpdateVel_reference
+$(objEXETempDir)/MaestroConvert.o: CPPFLAGS += -DConvertRhoXToX=ConvertRhoXToX_reference -DConvertRhoHToH=ConvertRhoHToH_reference -DPutInPertForm=PutInPertForm_reference
+$(objEXETempDir)/MaestroForce.o: CPPFLAGS += -DModifyScalForce=ModifyScalForce_reference
+$(objEXETempDir)/MaestroFill3dData.o: CPPFLAGS += -DPut1dArrayOnCart=Put1dArrayOnCart_reference -DAddw0=Addw0_reference -DMakeW0mac=MakeW0mac_reference -DMakeS0mac=MakeS0mac_reference
+"""
+assert key in mk
+open("GNUmakefile", "w").write(mk.replace(key, add + key) + tail)
+EOF3
+$MK > build_cx.log 2>&1 || { tail -30 build_cx.log; exit 1; }
+cp "Maestro${DIM}d.gnu.OMP.ex" "$OUT/Maestro${DIM}d$SUF.cx.ex"
+
 # 3. fcompare
 if [ ! -d "$WORK/plotfile" ]; then cp -r "$REF/external/amrex/Tools/Plotfile" "$WORK/plotfile"; fi
 (cd "$WORK/plotfile" && make -j$J AMREX_HOME=$REF/external/amrex DIM=$DIM USE_MPI=FALSE COMP=gnu \

@@ -66,9 +66,18 @@ static B3 nodal_box(const MxGeom* g, int dir, int ng) {
         for (int j = (b).lo[1]; j <= (b).hi[1]; ++j) \
             for (int i = (b).lo[0]; i <= (b).hi[0]; ++i)
 
+/* std::min / std::max semantics (amrex::min/max) */
+static inline double dmin(double a, double b) { return (b < a) ? b : a; }
+static inline double dmax(double a, double b) { return (a < b) ? b : a; }
+
+/* QuadInterp with its default limit = true (Source/Maestro.H:65-68: every call site on this path
+ * leaves the argument out), Source/MaestroFill3dData.cpp:339-355 */
 static double quad_interp(double x, double x0, double x1, double x2, double y0, double y1, double y2) {
-    return y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
-           ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+    double y = y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
+               ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+    if (y > dmax(y0, dmax(y1, y2))) y = dmax(y0, dmax(y1, y2));
+    if (y < dmin(y0, dmin(y1, y2))) y = dmin(y0, dmin(y1, y2));
+    return y;
 }
 
 /* s0(r) of a 1-D array with component stride st */
@@ -195,7 +204,8 @@ int orc_put_in_pert_form(const MxGeom* g, const MxFab* scal, const MxBase* s0, i
 
 int orc_modify_scal_force(const MxGeom* g, const MxFab* scal_force, const MxFab* state, const MxFab* umac,
                           const MxBase* s0_edge, int lev, const MxFab* s0_cart, const MxFab* w0_cart,
-                          const double* w0, int comp, int fullform, int bcf_hi, const MxSphr* S) {
+                          const double* w0, int comp, int fullform, int bcf_hi, const MxFab* s0_edge_cart,
+                          const MxSphr* S) {
     V f = view(scal_force), sc = view(state), s0c = view(s0_cart);
     V um = view(&umac[0]), vm = view(&umac[1]), wm = view(&umac[g->dim == 3 ? 2 : 1]);
     B3 b = valid_box(g);
@@ -236,14 +246,23 @@ int orc_modify_scal_force(const MxGeom* g, const MxFab* scal_force, const MxFab*
     }
     V w0c = view(w0_cart);
     const int last = g->dim - 1;
-    const int st = s0_edge->nvar;
-    const double* s0 = s0_edge->p + (long)lev * s0_edge->len * s0_edge->nvar;
+    const int st = s0_edge_cart ? 1 : s0_edge->nvar;
+    const double* s0 = s0_edge_cart ? NULL : s0_edge->p + (long)lev * s0_edge->len * s0_edge->nvar;
+    V ec = s0c;
+    if (s0_edge_cart) ec = view(s0_edge_cart);
     FOR_BOX(b) {
         const int r = g->dim == 2 ? j : k;
         /* s0_edge_cart: Put1dArrayOnCart(s0_edge, ., false, false, bcs_f) on a 1-ghost MultiFab */
-        int rp = r + 1;
-        if (r == g->dom_hi[last]) rp = bcf_hi == MX_BC_INT_DIR ? g->dom_lo[last] : g->dom_hi[last];
-        const double e_lo = S0(r), e_hi = S0(rp);
+        double e_lo, e_hi;
+        if (s0_edge_cart) {
+            e_lo = A(ec, i, j, k, 0);
+            e_hi = g->dim == 2 ? A(ec, i, j + 1, k, 0) : A(ec, i, j, k + 1, 0);
+        } else {
+            int rp = r + 1;
+            if (r == g->dom_hi[last]) rp = bcf_hi == MX_BC_INT_DIR ? g->dom_lo[last] : g->dom_hi[last];
+            e_lo = S0(r);
+            e_hi = S0(rp);
+        }
         const double c = A(s0c, i, j, k, 0);
         if (g->dim == 2) {
             double divu = (A(um, i + 1, j, k, 0) - A(um, i, j, k, 0)) / dx[0] +
@@ -359,14 +378,19 @@ static double s0_cart_at(const MxSphr* S, const MxGeom* g, const double* s0, int
     return interp_cc(S, s0, st, S->s0_interp_type, sqrt(x * x + y * y + z * z));
 }
 
-int orc_make_s0mac(const MxGeom* g, const MxBase* b0, const MxFab* s0mac, const MxSphr* S) {
+int orc_make_s0mac(const MxGeom* g, const MxBase* b0, const MxFab* s0mac, const MxFab* s0_cart,
+                   const MxSphr* S) {
     const int type = S->s0mac_interp_type;
     const int st = b0->nvar;
     const double* s0 = b0->p;
     for (int d = 0; d < 3; ++d) {
         V m = view(&s0mac[d]);
         B3 b = nodal_box(g, d, 1);
-        if (type == 1) {
+        if (type == 1 && s0_cart) {
+            V c = view(s0_cart);
+            FOR_BOX(b)
+            A(m, i, j, k, 0) = 0.5 * (A(c, i - (d == 0), j - (d == 1), k - (d == 2), 0) + A(c, i, j, k, 0));
+        } else if (type == 1) {
             FOR_BOX(b)
             A(m, i, j, k, 0) = 0.5 * (s0_cart_at(S, g, s0, st, i - (d == 0), j - (d == 1), k - (d == 2)) +
                                       s0_cart_at(S, g, s0, st, i, j, k));

@@ -546,7 +546,8 @@ int DRV(put_in_pert_form)(const MxGeom* g, const MxFab* scal, const MxBase* s0, 
 int DRV(modify_scal_force)(const MxGeom* g, const MxFab* scal_force, const MxFab* state,
                            const MxFab* umac, const MxBase* s0_edge, int lev, const MxFab* s0_cart,
                            const MxFab* w0_cart, const double* w0, int comp, int fullform,
-                           int bcf_hi, const MxSphr* S) {
+                           int bcf_hi, const MxFab* /*s0_edge_cart: built inside the reference*/,
+                           const MxSphr* S) {
     Maestro m;
     setup(m, g);
     SphrGeom sg;
@@ -610,7 +611,8 @@ int DRV(make_w0mac)(const MxGeom* g, const MxFab* w0mac, const MxFab* w0_cart, c
 // Maestro::MakeS0mac, Source/MaestroFill3dData.cpp:712.  s0mac_interp_type 1 reads the 2-ghost
 // s0_cart temporary after FillPatch(bcs_f): the shim's FillPatch hook fills it by first-order
 // extrapolation (the reference's bcs_f fill at outflow faces).
-int DRV(make_s0mac)(const MxGeom* g, const MxBase* s0, const MxFab* s0mac, const MxSphr* S) {
+int DRV(make_s0mac)(const MxGeom* g, const MxBase* s0, const MxFab* s0mac,
+                    const MxFab* /*s0_cart: built inside the reference*/, const MxSphr* S) {
     Maestro m;
     setup(m, g);
     SphrGeom sg;

@@ -115,7 +115,7 @@ def run_pert(calls, dim, flag, sph, s0t=3, mv=identity, back=identity):
     return [back(d).data]
 
 
-def run_force(calls, dim, fullform, bcf, sph, s0t=3, pad=(0, 0, 0), mv=identity, back=identity):
+def run_force(calls, dim, fullform, bcf, sph, s0t=3, pad=(0, 0, 0), ecfab=False, mv=identity, back=identity):
     p = Prob(dim, (12, 10, 14)[:dim], 14, dom_pad=pad, spherical=sph)
     force = p.cell(NSCAL, 1, -1.0, 1.0)
     state = p.cell(NSCAL, 3)
@@ -124,10 +124,11 @@ def run_force(calls, dim, fullform, bcf, sph, s0t=3, pad=(0, 0, 0), mv=identity,
     s0_cart = p.cell(1, 1)
     w0_cart = p.cell(dim, 2, -0.3, 0.3)
     w0 = rnd(p.rng, (p.nr + 1,), -0.3, 0.3)
+    ec = p.cell(1, 1)  # the reference's s0_edge_cart temporary as an AMR caller would pass it
     d = mv(force)
     calls.modify_scal_force(p.geom, d, mv(state), [mv(u) for u in umac], s0_edge, 0, mv(s0_cart),
                             None if sph else mv(w0_cart), w0 if sph else None, RHO, fullform, bcf,
-                            p.S(s0_interp_type=s0t))
+                            p.S(s0_interp_type=s0t), s0_edge_cart=mv(ec) if ecfab else None)
     return [back(d).data]
 
 
@@ -151,12 +152,14 @@ def run_w0mac(calls, w0mt, pad=(0, 0, 0), mv=identity, back=identity):
     return [back(w).data for w in d]
 
 
-def run_s0mac(calls, s0mt, s0t, pad=(0, 0, 0), mv=identity, back=identity):
+def run_s0mac(calls, s0mt, s0t, pad=(0, 0, 0), cartfab=False, mv=identity, back=identity):
     p = Prob(3, (12, 10, 14), 17, dom_pad=pad, spherical=True)
     sm = p.faces(1, 1)
     s0 = p.base(p.nr)
+    cart = p.cell(1, 2)
     d = [mv(w) for w in sm]
-    calls.make_s0mac(p.geom, s0, d, p.S(s0mac_interp_type=s0mt, s0_interp_type=s0t))
+    calls.make_s0mac(p.geom, s0, d, p.S(s0mac_interp_type=s0mt, s0_interp_type=s0t),
+                     s0_cart=mv(cart) if cartfab else None)
     return [back(w).data for w in d]
 
 
@@ -219,6 +222,10 @@ GPU_ONLY = [
     ("force-sph-inner", run_force, dict(dim=3, fullform=0, bcf=BC_FOEXTRAP, sph=True, pad=(2, 3, 4))),
     ("s0mac-t1-inner", run_s0mac, dict(s0mt=1, s0t=3, pad=(2, 3, 4))),
     ("w0mac-t4-inner", run_w0mac, dict(w0mt=4, pad=(2, 3, 4))),
+    # AMR callers hand the reference's internal temporaries in as fabs (after their own FillPatch)
+    ("force-3d-ecfab", run_force, dict(dim=3, fullform=0, bcf=BC_FOEXTRAP, sph=False, pad=(2, 3, 4), ecfab=True)),
+    ("force-2d-ecfab", run_force, dict(dim=2, fullform=0, bcf=BC_FOEXTRAP, sph=False, ecfab=True)),
+    ("s0mac-t1-cartfab", run_s0mac, dict(s0mt=1, s0t=3, pad=(2, 3, 4), cartfab=True)),
 ]
 
 

@@ -51,5 +51,8 @@ def test_reference_build_reproduces_ci_extrema(tmp_path):
 
 
 @pytest.mark.gpu
-def test_overlay_build_reproduces_ci_extrema(tmp_path):
-    assert _extrema("Maestro2d.mx.ex", str(tmp_path)) == open(GOLDEN).read()
+@pytest.mark.parametrize("exe", ["Maestro2d.mx.ex", "Maestro2d.cx.ex"])
+def test_overlay_build_reproduces_ci_extrema(tmp_path, exe):
+    """mx: maestroex_b200/overlay; cx: + overlay_companions (conversions, forcing, base-state
+    mappings and UpdateVel on the GPU as well)"""
+    assert _extrema(exe, str(tmp_path)) == open(GOLDEN).read()

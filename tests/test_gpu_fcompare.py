@@ -91,6 +91,12 @@ def parse_fcompare(text):
     (3, "fx", ("maestro.ppm_type=2", "amr.n_cell=32 32 256")),
     # boxes of 32 x 32 x 64: the host-fab z-slab pipeline runs with two slabs per box
     (3, "fx", ("amr.n_cell=32 32 256", "amr.max_grid_size=64")),
+    # arm "cx": overlay (+ overlay_fused in 3-D) + overlay_companions, i.e. ALSO ConvertRhoXToX /
+    # ConvertRhoHToH / PutInPertForm, ModifyScalForce, Put1dArrayOnCart, Addw0 and UpdateVel on
+    # libmxadv.so inside the real time step
+    (2, "cx", ()),
+    (2, "cx", ("maestro.ppm_type=1",)),
+    (3, "cx", ("amr.n_cell=32 32 256",)),
 ])
 def test_fcompare_10_steps(tmp_path, tmp_path_factory, dim, arm, extra):
     for f in (f"Maestro{dim}d.ref.ex", f"Maestro{dim}d.{arm}.ex", f"fcompare{dim}d.ex",
@@ -112,7 +118,7 @@ def test_fcompare_10_steps(tmp_path, tmp_path_factory, dim, arm, extra):
     keep = os.environ.get("MXADV_FCOMPARE_OUT")
     if keep:
         os.makedirs(keep, exist_ok=True)
-        tag = f"{dim}d" + ("" if arm == "mx" else "_fused") + "".join("_" + e.split(".")[-1].replace(" ", "x") for e in extra)
+        tag = f"{dim}d" + {"mx": "", "fx": "_fused", "cx": "_companions"}[arm] + "".join("_" + e.split(".")[-1].replace(" ", "x") for e in extra)
         open(os.path.join(keep, f"fcompare_{tag}.txt"), "w").write(table_txt + r.stderr)
     errs = parse_fcompare(table_txt)
     assert len(errs) >= 20, table_txt[-3000:]
@@ -125,6 +131,7 @@ def test_fcompare_10_steps(tmp_path, tmp_path_factory, dim, arm, extra):
     ("fx", ()),
     ("fx", ("maestro.ppm_type=1",)),
     ("mx", ("maestro.ppm_type=2",)),
+    ("cx", ()),   # + MakeW0mac / MakeS0mac / spherical Put1dArrayOnCart / Addw0 / UpdateVel on the GPU
 ])
 def test_fcompare_wdconvect(tmp_path, tmp_path_factory, arm, extra):
     """BASELINE config 3 as an application: wdconvect (spherical base state, all-outflow) with
