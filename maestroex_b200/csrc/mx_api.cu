@@ -536,6 +536,10 @@ int fill_kflux(Session& S, const MxFluxParams* p, const MxBase* rho0_old,
     f->num_spec = p->num_spec;
     f->start_comp = p->start_comp;
     f->num_comp = p->num_comp;
+    // spherical: the 1-D arrays have ONE radial level whatever the AMR level and the flux forms
+    // read the base state from the face arrays (r0mac / h0mac), never from these
+    // (Source/MaestroMakeFlux.cpp:311-407, :788-1021): not staged at all
+    if (p->spherical) return MX_OK;
     MX_TRY(S.base(rho0_old, p->lev, &f->rho0_old, &f->st_rho0_old));
     MX_TRY(S.base(rho0_new, p->lev, &f->rho0_new, &f->st_rho0_new));
     MX_TRY(S.base(rho0_edge_old, p->lev, &f->rho0_edge_old, &f->st_rho0_edge_old));

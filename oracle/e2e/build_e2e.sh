@@ -129,14 +129,22 @@ if [ ! -d "$WORK/plotfile" ]; then cp -r "$REF/external/amrex/Tools/Plotfile" "$
 (cd "$WORK/plotfile" && make -j$J AMREX_HOME=$REF/external/amrex DIM=$DIM USE_MPI=FALSE COMP=gnu \
     programs=fcompare > build.log 2>&1)
 cp "$WORK/plotfile/fcompare.gnu.ex" "$OUT/fcompare${DIM}d.ex"
+# 3b. fextrema (the tool of the reference's CI goldens, .github/workflows/*-compare.yml); the
+#     executable name does not carry the dimension, so force the relink
+rm -f "$WORK/plotfile/fextrema.gnu.ex"
+(cd "$WORK/plotfile" && make -j$J AMREX_HOME=$REF/external/amrex DIM=$DIM USE_MPI=FALSE COMP=gnu \
+    programs=fextrema > build_fextrema.log 2>&1)
+cp "$WORK/plotfile/fextrema.gnu.ex" "$OUT/fextrema${DIM}d.ex"
 
 # 4. run-time data of the problem (inputs, initial model, EOS table; the table is 60 MB of
 #    text, shipped gzipped)
 if [ "$PROB" = wdconvect ]; then
     cp "$WORK/${TAGP}ref$DIM"/inputs_files/inputs_3d_regression "$OUT/inputs_3d_wdconvect"
+    cp "$WORK/${TAGP}ref$DIM"/inputs_files/inputs_3d_regression.2levels "$OUT/inputs_3d_wdconvect_2levels"
     cp "$WORK/${TAGP}ref$DIM"/model_files/kepler_new_6.25e8.hybrid.hse.320 "$OUT/"
 else
     cp "$WORK/${TAGP}ref$DIM"/inputs_${DIM}d_C "$WORK/${TAGP}ref$DIM"/model.hse.cool.coulomb "$OUT/"
+    [ "$DIM" = 2 ] && cp "$WORK/${TAGP}ref$DIM"/inputs_2d_regression "$OUT/"
 fi
 [ -f "$OUT/helm_table.dat.gz" ] || gzip -c "$REF/external/Microphysics/EOS/helmholtz/helm_table.dat" > "$OUT/helm_table.dat.gz"
 strip "$OUT"/*.ex
