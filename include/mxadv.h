@@ -267,6 +267,33 @@ int mx_make_w0_planar(const MxW0Params* par, const double* w0_old, const double*
                       const double* etarho_cc, double* w0, double* w0_force, double* p0bdot,
                       void* stream);
 
+/* base_geom of a MULTILEVEL planar base state (Source/BaseStateGeometry.H:22-44): radial level n
+ * has nr[n] cells of width dr[n] (nr[n] = nr_fine / 2^(max_radial_level-n)) and is defined on
+ * numdisjointchunks[n] chunks [r_start_coord(n,j), r_end_coord(n,j)], j = 1 .. chunks; entry (n,j)
+ * of the two coordinate tables is at [n*chunk_len + j] (the reference's BaseStateArray layout). */
+typedef struct MxRadialGeom {
+    int max_radial_level, finest_radial_level, nr_fine;
+    const double* dr;                     /* [max_radial_level+1] */
+    const int* nr;                        /* [max_radial_level+1] */
+    const int* base_cutoff_density_coord; /* [max_radial_level+1] */
+    const int* numdisjointchunks;         /* [finest_radial_level+1] */
+    const int* r_start_coord;             /* [(finest_radial_level+1) * chunk_len] */
+    const int* r_end_coord;
+    int chunk_len;
+} MxRadialGeom;
+
+/* Maestro::Makew0 -> Makew0Planar for a multilevel base state (Source/MaestroMakew0.cpp:60-272
+ * with the level loop, the restriction / offset of :185-213, the zeroing of :216-236 and the
+ * RestrictBase / FillGhostBase calls, Source/MaestroBaseStateGeometry.cpp:236-355).  Every 1-D
+ * array is the reference's BaseState: (max_radial_level+1) levels x nr_fine cells (w0_old / w0:
+ * nr_fine+1 edges), level n at offset n*len.  par->dr / base_cutoff_density_coord are not read
+ * (they come per level from rg).  HOST arrays (they are a few kB; staged by the library). */
+int mx_make_w0_planar_ml(const MxW0Params* par, const MxRadialGeom* rg, const double* w0_old,
+                         const double* Sbar, const double* p0_old, const double* p0_new,
+                         const double* gamma1bar_old, const double* gamma1bar_new,
+                         const double* p0_minus_peosbar, const double* etarho_cc, double* w0,
+                         double* w0_force, double* p0bdot, void* stream);
+
 /* Replaces Maestro::Makew0 -> Makew0Sphr (Source/MaestroMakew0.cpp:537-740) including the
  * calls it makes: MakeGravEdge, spherical branch (Source/MaestroMakeGrav.cpp:303-322) and
  * Tridiag (:942-969).  r_cc_loc (nr_fine) and r_edge_loc (nr_fine+1) are level 0 of

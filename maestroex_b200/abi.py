@@ -355,5 +355,40 @@ class Sphr:
         return p
 
 
+class MxRadialGeom(C.Structure):
+    _fields_ = [
+        ("max_radial_level", C.c_int), ("finest_radial_level", C.c_int), ("nr_fine", C.c_int),
+        ("dr", C.c_void_p), ("nr", C.c_void_p), ("base_cutoff_density_coord", C.c_void_p),
+        ("numdisjointchunks", C.c_void_p), ("r_start_coord", C.c_void_p), ("r_end_coord", C.c_void_p),
+        ("chunk_len", C.c_int),
+    ]
+
+
+@dataclass
+class RadialGeom:
+    """base_geom of a multilevel planar base state (Source/BaseStateGeometry.H); numpy arrays:
+    dr float64 [nlev], nr / base_cutoff_density_coord int32 [nlev], numdisjointchunks int32 [nfine],
+    r_start_coord / r_end_coord int32 [nfine, chunk_len] (entry (n, j), j = 1 .. chunks)."""
+    nr_fine: int
+    dr: object
+    nr: object
+    base_cutoff_density_coord: object
+    numdisjointchunks: object
+    r_start_coord: object
+    r_end_coord: object
+
+    def c(self) -> MxRadialGeom:
+        g = MxRadialGeom()
+        g.max_radial_level = len(self.dr) - 1
+        g.finest_radial_level = len(self.numdisjointchunks) - 1
+        g.nr_fine = self.nr_fine
+        for k in ("dr", "nr", "base_cutoff_density_coord", "numdisjointchunks", "r_start_coord", "r_end_coord"):
+            a = getattr(self, k)
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.float64 if k == "dr" else np.int32), k
+            setattr(g, k, a.ctypes.data)
+        g.chunk_len = int(self.r_start_coord.shape[1])
+        return g
+
+
 def byref_or_null(x):
     return C.byref(x) if x is not None else None

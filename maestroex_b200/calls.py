@@ -127,6 +127,20 @@ class Calls:
             v(etarho_ec), v(r_cc_loc), v(r_edge_loc), v(w0), v(w0_force), *self._tail(stream))
         self._check(rc, "make_w0_sphr")
 
+    def make_w0_planar_ml(self, par, rg, w0_old, Sbar, p0_old, p0_new, gamma1bar_old, gamma1bar_new,
+                          p0_minus_peosbar, etarho_cc, w0, w0_force, stream: int = 0):
+        """Makew0Planar for a multilevel base state (host numpy arrays, shape (nlev, len));
+        returns p0bdot."""
+        p, g = par.c(), rg.c()
+        pb = C.c_double(0.0)
+        v = self._vp
+        rc = self._fn("make_w0_planar_ml")(
+            C.byref(p), C.byref(g), v(w0_old), v(Sbar), v(p0_old), v(p0_new), v(gamma1bar_old),
+            v(gamma1bar_new), v(p0_minus_peosbar), v(etarho_cc), v(w0), v(w0_force), C.byref(pb),
+            *self._tail(stream))
+        self._check(rc, "make_w0_planar_ml")
+        return pb.value
+
     # -- Maestro::UpdateScal ----------------------------------------------------------
     def update_scal(self, geom: Geom, stateold: Fab, statenew: Fab, sflux, force: Fab, par,
                     eos_mask=None, p0_cart: Fab = None, stream: int = 0):

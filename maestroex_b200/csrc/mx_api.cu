@@ -1778,3 +1778,70 @@ int mx_enthalpy_advance(const MxGeom* geom, const MxFab* state, const MxFab* sne
 }
 
 }  // extern "C"
+
+extern "C" int mx_make_w0_planar_ml(const MxW0Params* par, const MxRadialGeom* rg, const double* w0_old,
+                                    const double* Sbar, const double* p0_old, const double* p0_new,
+                                    const double* gamma1bar_old, const double* gamma1bar_new,
+                                    const double* p0_minus_peosbar, const double* etarho_cc, double* w0,
+                                    double* w0_force, double* p0bdot, void* stream) {
+    if (!par || !rg || !w0_old || !Sbar || !p0_old || !p0_new || !gamma1bar_old || !gamma1bar_new ||
+        !p0_minus_peosbar || !etarho_cc || !w0 || !w0_force)
+        return fail(MX_ERR_INVALID, "null argument");
+    const int nlev = rg->max_radial_level + 1, nf = rg->finest_radial_level + 1;
+    if (rg->nr_fine < 2 || nlev < 1 || nf < 1 || nf > nlev || rg->chunk_len < 2 || !rg->dr || !rg->nr ||
+        !rg->base_cutoff_density_coord || !rg->numdisjointchunks || !rg->r_start_coord || !rg->r_end_coord)
+        return fail(MX_ERR_INVALID, "MxRadialGeom is incomplete");
+    for (int n = 0; n < nf; ++n) {
+        if (rg->numdisjointchunks[n] < 1 || rg->numdisjointchunks[n] >= rg->chunk_len)
+            return fail(MX_ERR_INVALID, "numdisjointchunks(%d) does not fit the coordinate tables", n);
+        for (int j = 1; j <= rg->numdisjointchunks[n]; ++j) {
+            const int lo = rg->r_start_coord[n * rg->chunk_len + j], hi = rg->r_end_coord[n * rg->chunk_len + j];
+            if (lo < 0 || hi < lo || hi >= rg->nr[n] || rg->nr[n] > rg->nr_fine)
+                return fail(MX_ERR_INVALID, "chunk %d of radial level %d is outside the level", j, n);
+        }
+    }
+    MX_TRY(require_device());
+    Session S(stream);
+    const size_t lc = (size_t)nlev * rg->nr_fine, le = (size_t)nlev * (rg->nr_fine + 1);
+    auto up = [&](const void* h, size_t bytes, const void** d) -> int {
+        void* p = nullptr;
+        CUDA_OK(S.alloc(&p, bytes));
+        CUDA_OK(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, S.stream()));
+        *d = p;
+        return MX_OK;
+    };
+    const void *d_dr, *d_nr, *d_cut, *d_nc, *d_rs, *d_re, *d_w0o, *d_S, *d_p0o, *d_p0n, *d_g1o, *d_g1n, *d_pmp, *d_ecc;
+    MX_TRY(up(rg->dr, sizeof(double) * nlev, &d_dr));
+    MX_TRY(up(rg->nr, sizeof(int) * nlev, &d_nr));
+    MX_TRY(up(rg->base_cutoff_density_coord, sizeof(int) * nlev, &d_cut));
+    MX_TRY(up(rg->numdisjointchunks, sizeof(int) * nf, &d_nc));
+    MX_TRY(up(rg->r_start_coord, sizeof(int) * nf * rg->chunk_len, &d_rs));
+    MX_TRY(up(rg->r_end_coord, sizeof(int) * nf * rg->chunk_len, &d_re));
+    MX_TRY(up(w0_old, sizeof(double) * le, &d_w0o));
+    MX_TRY(up(Sbar, sizeof(double) * lc, &d_S));
+    MX_TRY(up(p0_old, sizeof(double) * lc, &d_p0o));
+    MX_TRY(up(p0_new, sizeof(double) * lc, &d_p0n));
+    MX_TRY(up(gamma1bar_old, sizeof(double) * lc, &d_g1o));
+    MX_TRY(up(gamma1bar_new, sizeof(double) * lc, &d_g1n));
+    MX_TRY(up(p0_minus_peosbar, sizeof(double) * lc, &d_pmp));
+    MX_TRY(up(etarho_cc, sizeof(double) * lc, &d_ecc));
+    void *d_w0, *d_f, *d_scr, *d_pb;
+    CUDA_OK(S.alloc(&d_w0, sizeof(double) * le));
+    CUDA_OK(S.alloc(&d_f, sizeof(double) * lc));
+    CUDA_OK(S.alloc(&d_scr, sizeof(double) * (2 * (size_t)rg->nr_fine + 4)));
+    CUDA_OK(S.alloc(&d_pb, sizeof(double)));
+    CUDA_OK(cudaMemsetAsync(d_pb, 0, sizeof(double), S.stream()));
+    w0_planar_ml(*par, rg->max_radial_level, rg->finest_radial_level, rg->nr_fine, rg->chunk_len,
+                 (const double*)d_dr, (const int*)d_nr, (const int*)d_cut, (const int*)d_nc, (const int*)d_rs,
+                 (const int*)d_re, (const double*)d_w0o, (const double*)d_S, (const double*)d_p0o,
+                 (const double*)d_p0n, (const double*)d_g1o, (const double*)d_g1n, (const double*)d_pmp,
+                 (const double*)d_ecc, (double*)d_w0, (double*)d_f, (double*)d_scr, (double*)d_pb, S.stream());
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(w0, d_w0, sizeof(double) * le, cudaMemcpyDeviceToHost, S.stream()));
+    CUDA_OK(cudaMemcpyAsync(w0_force, d_f, sizeof(double) * lc, cudaMemcpyDeviceToHost, S.stream()));
+    double pb = 0.0;
+    CUDA_OK(cudaMemcpyAsync(&pb, d_pb, sizeof(double), cudaMemcpyDeviceToHost, S.stream()));
+    CUDA_OK(cudaStreamSynchronize(S.stream()));
+    if (p0bdot && par->add_pb) *p0bdot = pb;
+    return MX_OK;
+}

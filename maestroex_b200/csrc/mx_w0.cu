@@ -330,3 +330,183 @@ void w0_sphr(const MxW0Params& P, const double* w0_old, const double* Sbar,
                                                       re, w0, w0_force, scratch, status_dev);
     mx_count_launch();
 }
+
+// ---- multilevel planar Makew0 (MaestroMakew0.cpp:60-272 with max_radial_level > 0, plus
+// RestrictBase / FillGhostBase, MaestroBaseStateGeometry.cpp:236-355) ---------------------------
+// The level loop is a chain of short serial recurrences coupled through restriction and offsets;
+// one thread walks it (a few thousand steps), the block's other threads only take part in the
+// per-cell w0_force loop.
+namespace {
+struct KRadial {
+    int max_lev, finest_lev, nrf, chunk_len;
+    const double* dr;
+    const int *nr, *cut, *nchunk, *rs, *re;
+};
+#define RS_(n, j) (G.rs[(n) * G.chunk_len + (j)])
+#define RE_(n, j) (G.re[(n) * G.chunk_len + (j)])
+
+__device__ double ml_dmin(double a, double b) { return (b < a) ? b : a; }
+__device__ double ml_slope(const double* c, int r) {
+    const double del = 0.5 * (c[r + 1] - c[r - 1]);
+    const double dpls = 2.0 * (c[r + 1] - c[r]);
+    const double dmn = 2.0 * (c[r] - c[r - 1]);
+    double slim = ml_dmin(fabs(dpls), fabs(dmn));
+    slim = dpls * dmn > 0.0 ? slim : 0.0;
+    return copysign(1.0, del) * ml_dmin(slim, fabs(del));
+}
+__device__ void ml_restrict(const KRadial& G, double* s0, int len, bool cc) {
+    for (int n = G.finest_lev; n >= 1; --n)
+        for (int i = 1; i <= G.nchunk[n]; ++i) {
+            double *f = s0 + (long)n * len, *c = s0 + (long)(n - 1) * len;
+            if (cc) {
+                for (int j = RS_(n, i); j < RE_(n, i); j += 2) c[j / 2] = 0.5 * (f[j] + f[j + 1]);
+            } else {
+                for (int j = RS_(n, i); j <= RE_(n, i) + 1; j += 2) c[j / 2] = f[j];
+            }
+        }
+}
+__device__ void ml_fill_ghost(const KRadial& G, double* s0, int len, bool cc) {
+    for (int n = G.finest_lev; n >= 1; --n)
+        for (int i = 1; i <= G.nchunk[n]; ++i) {
+            const int lo = RS_(n, i), hi = RE_(n, i);
+            double *f = s0 + (long)n * len, *c = s0 + (long)(n - 1) * len;
+            if (cc) {
+                if (lo != 0) {
+                    int rc = lo / 2 - 1;
+                    double sl = ml_slope(c, rc);
+                    f[lo - 1] = c[rc] + 0.25 * sl;
+                    f[lo - 2] = c[rc] - 0.25 * sl;
+                    rc = lo / 2 - 2;
+                    sl = ml_slope(c, rc);
+                    f[lo - 3] = c[rc] + 0.25 * sl;
+                    f[lo - 4] = c[rc] - 0.25 * sl;
+                }
+                if (hi != G.nr[n] - 1) {
+                    int rc = (hi + 1) / 2;
+                    double sl = ml_slope(c, rc);
+                    f[hi + 1] = c[rc] - 0.25 * sl;
+                    f[hi + 2] = c[rc] + 0.25 * sl;
+                    rc = (hi + 1) / 2 + 1;
+                    sl = ml_slope(c, rc);
+                    f[hi + 3] = c[rc] - 0.25 * sl;
+                    f[hi + 4] = c[rc] + 0.25 * sl;
+                }
+            } else {
+                if (lo != 0) {
+                    f[lo - 1] = -f[lo + 1] / 3.0 + f[lo] + c[lo / 2 - 1] / 3.0;
+                    f[lo - 2] = c[(lo - 2) / 2];
+                }
+                if (hi + 1 != G.nr[n]) {
+                    f[hi + 2] = -f[hi] / 3.0 + f[hi + 1] + c[(hi + 3) / 2] / 3.0;
+                    f[hi + 3] = c[(hi + 3) / 2];
+                }
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_w0_planar_ml(const MxW0Params P, const KRadial G, const double* __restrict__ w0_old,
+               const double* __restrict__ Sbar, const double* __restrict__ p0_old,
+               const double* __restrict__ p0_new, const double* __restrict__ g1o,
+               const double* __restrict__ g1n, const double* __restrict__ pmp,
+               const double* __restrict__ etarho_cc, double* w0, double* w0_force, double* scratch,
+               double* p0bdot_out) {
+    const int nrf = G.nrf, lc = nrf, le = nrf + 1, nlev = G.max_lev + 1;
+    double* psi = scratch;
+    double* int1 = scratch + nrf + 1;
+    for (long q = threadIdx.x; q < (long)nlev * le; q += blockDim.x) w0[q] = 0.0;       // :87
+    for (long q = threadIdx.x; q < (long)nlev * lc; q += blockDim.x) w0_force[q] = 0.0;  // Makew0 :18
+    __syncthreads();
+#define W_(n, r) w0[(long)(n) * le + (r)]
+#define C_(a, n, r) a[(long)(n) * lc + (r)]
+    if (threadIdx.x == 0) {
+        for (int n = 0; n <= G.max_lev; ++n) {
+            for (int r = 0; r < nrf; ++r) psi[r] = 0.0;
+            const int cut = G.cut[n];
+            const double dr = G.dr[n];
+            for (int j = 1; j <= G.nchunk[n]; ++j) {
+                if (n == 0) {
+                    W_(0, 0) = 0.0;
+                    int1[0] = 0.0;
+                } else {
+                    W_(n, RS_(n, j)) = W_(n - 1, RS_(n, j) / 2);
+                }
+                for (int r = RS_(n, j); r <= RE_(n, j); ++r)
+                    if (r < cut) psi[r] = C_(etarho_cc, n, r) * fabs(P.grav_const);
+                for (int r = RS_(n, j) + 1; r <= RE_(n, j) + 1; ++r) {
+                    const double gavg = (C_(g1o, n, r - 1) + C_(g1n, n, r - 1)) *
+                                        (C_(p0_old, n, r - 1) + C_(p0_new, n, r - 1)) / 4.0;
+                    double dchi = 0.0;
+                    if (r < cut) {
+                        if (P.is_predictor)
+                            dchi = P.dpdt_factor * C_(pmp, n, r - 1) / (C_(g1o, n, r - 1) * C_(p0_old, n, r - 1) * P.dt);
+                        else
+                            dchi += P.dpdt_factor * C_(pmp, n, r - 1) / (C_(g1n, n, r - 1) * C_(p0_new, n, r - 1) * P.dt);
+                    }
+                    if (n == 0) int1[r] = int1[r - 1] + (1.0 / gavg) * dr;
+                    W_(n, r) = W_(n, r - 1) + C_(Sbar, n, r - 1) * dr - psi[r - 1] / gavg * dr - dchi * dr;
+                }
+                if (n == 0 && P.add_pb) {
+                    const int k = RE_(n, j) + 1;
+                    const double pb = W_(n, k) / int1[k];
+                    if (p0bdot_out) *p0bdot_out = pb;
+                    for (int r = RS_(n, j) + 1; r <= RE_(n, j) + 1; ++r) W_(n, r) -= pb * int1[r];
+                }
+                if (n > 0) {
+                    const double offset = W_(n, RE_(n, j) + 1) - W_(n - 1, (RE_(n, j) + 1) / 2);
+                    for (int i = n - 1; i >= 0; --i) {
+                        const int refrat = 1 << (n - i);
+                        // QUIRK :196: the restriction writes level n, not level i
+                        for (int r = RS_(n, j); r <= RE_(n, j) + 1; ++r)
+                            if (r % refrat == 0) W_(n, r / refrat) = W_(n, r);
+                        for (int r = (RE_(n, j) + 1) / refrat + 1; r <= G.nr[i]; ++r) W_(i, r) += offset;
+                    }
+                }
+            }
+        }
+        for (int n = 1; n <= G.max_lev; ++n)
+            for (int j = 1; j <= G.nchunk[n]; ++j) {
+                const int lo = RE_(n, j) + 2;
+                const int hi = j == G.nchunk[n] ? G.nr[n] : RS_(n, j + 1) - 1;
+                for (int r = lo; r <= hi; ++r) W_(n, r) = 0.0;
+            }
+        ml_restrict(G, w0, le, false);
+        ml_fill_ghost(G, w0, le, false);
+    }
+    __syncthreads();
+    const double dt_in = P.dt_in, dtold_in = P.dtold_in;
+    const double dt_avg = 0.5 * (dt_in + dtold_in);
+    for (int n = 0; n <= G.max_lev; ++n)
+        for (int j = 1; j <= G.nchunk[n]; ++j)
+            for (int r = RS_(n, j) + threadIdx.x; r <= RE_(n, j); r += blockDim.x) {
+                const double* wo = w0_old + (long)n * le;
+                const double w0_old_cen = 0.5 * (wo[r] + wo[r + 1]);
+                const double w0_new_cen = 0.5 * (W_(n, r) + W_(n, r + 1));
+                const double w0_avg = 0.5 * (dt_in * w0_old_cen + dtold_in * w0_new_cen) / dt_avg;
+                const double div_avg =
+                    0.5 * (dt_in * (wo[r + 1] - wo[r]) + dtold_in * (W_(n, r + 1) - W_(n, r))) / dt_avg;
+                w0_force[(long)n * lc + r] = (w0_new_cen - w0_old_cen) / dt_avg + w0_avg * div_avg / G.dr[n];
+            }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ml_restrict(G, w0_force, lc, true);
+        ml_fill_ghost(G, w0_force, lc, true);
+    }
+#undef W_
+#undef C_
+}
+#undef RS_
+#undef RE_
+}  // namespace
+
+void w0_planar_ml(const MxW0Params& P, int max_lev, int finest_lev, int nrf, int chunk_len,
+                  const double* dr, const int* nr, const int* cut, const int* nchunk, const int* rs,
+                  const int* re, const double* w0_old, const double* Sbar, const double* p0_old,
+                  const double* p0_new, const double* g1o, const double* g1n, const double* pmp,
+                  const double* etarho_cc, double* w0, double* w0_force, double* scratch,
+                  double* p0bdot_dev, cudaStream_t stream) {
+    KRadial G{max_lev, finest_lev, nrf, chunk_len, dr, nr, cut, nchunk, rs, re};
+    k_w0_planar_ml<<<1, 256, 0, stream>>>(P, G, w0_old, Sbar, p0_old, p0_new, g1o, g1n, pmp, etarho_cc,
+                                         w0, w0_force, scratch, p0bdot_dev);
+    mx_count_launch();
+}

@@ -16,4 +16,10 @@ void w0_sphr(const MxW0Params& P, const double* w0_old, const double* Sbar,
              const double* etarho_cc, const double* etarho_ec, const double* rcc,
              const double* re, double* w0, double* w0_force, double* scratch, int* status_dev,
              bool irreg, cudaStream_t stream);
+void w0_planar_ml(const MxW0Params& P, int max_lev, int finest_lev, int nrf, int chunk_len,
+                  const double* dr, const int* nr, const int* cut, const int* nchunk, const int* rs,
+                  const int* re, const double* w0_old, const double* Sbar, const double* p0_old,
+                  const double* p0_new, const double* g1o, const double* g1n, const double* pmp,
+                  const double* etarho_cc, double* w0, double* w0_force, double* scratch,
+                  double* p0bdot_dev, cudaStream_t stream);
 #endif

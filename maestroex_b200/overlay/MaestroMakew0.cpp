@@ -1,9 +1,8 @@
 // Overlay for Source/MaestroMakew0.cpp: Maestro::Makew0 (Source/Maestro.H:1185-1196) and the
 // members that file defines, on libmxadv.so (mx_make_w0_planar / mx_make_w0_sphr).
-// (mx_make_w0_planar / mx_make_w0_sphr / mx_make_w0_sphr_irreg).  One radial level
-// (base_geom.max_radial_level == 0): the multilevel restriction / offset of Makew0Planar
-// (MaestroMakew0.cpp:185-236) and Makew0PlanarVarg are not on the accelerated path and abort
-// here (reference convention for illegal states; no CPU fallback).
+// (mx_make_w0_planar / mx_make_w0_planar_ml / mx_make_w0_sphr / mx_make_w0_sphr_irreg).
+// Makew0PlanarVarg (do_planar_invsq_grav / do_2d_planar_octant) is not on the accelerated path
+// and aborts here (reference convention for illegal states; no CPU fallback).
 #include <MxadvAmrex.H>
 
 using namespace amrex;
@@ -82,11 +81,42 @@ void Maestro::Makew0Planar(const BaseState<Real>& w0_old, BaseState<Real>& w0_fo
                            const BaseState<Real>& p0_minus_peosbar, const Real dt_in,
                            const Real dtold_in, const bool is_predictor) {
     BL_PROFILE_VAR("Maestro::Makew0Planar()", Makew0Planar);
-    if (base_geom.max_radial_level != 0 || base_geom.numdisjointchunks(0) != 1) {
-        Abort("libmxadv: Makew0Planar supports one radial level only");
-    }
     const MxW0Params p = w0_params(base_geom, dt, dt_in, dtold_in, is_predictor);
     Real pb = 0.0;
+    if (base_geom.max_radial_level != 0) {
+        // multilevel base state: level loop, restriction / offset, RestrictBase / FillGhostBase
+        // all inside the library (mx_make_w0_planar_ml); the BaseState arrays are passed whole
+        auto nr = base_geom.nr;
+        auto dr = base_geom.dr;
+        auto cut = base_geom.base_cutoff_density_coord;
+        auto ndc = base_geom.numdisjointchunks;
+        auto rs = base_geom.r_start_coord;
+        auto re = base_geom.r_end_coord;
+        MxRadialGeom rg;
+        rg.max_radial_level = base_geom.max_radial_level;
+        rg.finest_radial_level = base_geom.finest_radial_level;
+        rg.nr_fine = base_geom.nr_fine;
+        rg.dr = dr.dataPtr();
+        rg.nr = nr.dataPtr();
+        rg.base_cutoff_density_coord = cut.dataPtr();
+        rg.numdisjointchunks = ndc.dataPtr();
+        rg.r_start_coord = rs.dataPtr();
+        rg.r_end_coord = re.dataPtr();
+        rg.chunk_len = rs.length();
+#ifdef AMREX_USE_CUDA
+        Gpu::streamSynchronize();  // the 1-D arrays are managed memory read on the host side of the call
+#endif
+        mxadv::check(mx_make_w0_planar_ml(&p, &rg, row0(w0_old), row0(Sbar_in), row0(p0_old_in),
+                                          row0(p0_new_in), row0(gamma1bar_old_in), row0(gamma1bar_new_in),
+                                          row0(p0_minus_peosbar), row0(etarho_cc), row0(w0),
+                                          row0(w0_force), &pb, mxadv::stream()),
+                     "Makew0Planar (multilevel)");
+        if (add_pb) {
+            p0bdot = pb;
+            p0b = p0bdot * dt;
+        }
+        return;
+    }
     mxadv::check(mx_make_w0_planar(&p, row0(w0_old), row0(Sbar_in), row0(p0_old_in),
                                    row0(p0_new_in), row0(gamma1bar_old_in),
                                    row0(gamma1bar_new_in), row0(p0_minus_peosbar),

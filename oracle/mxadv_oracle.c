@@ -1381,3 +1381,156 @@ int orc_update_scal(const MxGeom* g, const MxFab* sold, const MxFab* snew, const
     if (n_eos) *n_eos = cnt;
     return 0;
 }
+
+/* ---- multilevel planar Makew0 ---------------------------------------------------------------
+ * Maestro::Makew0Planar with max_radial_level > 0 (Source/MaestroMakew0.cpp:60-272) and the
+ * RestrictBase / FillGhostBase it calls (Source/MaestroBaseStateGeometry.cpp:236-355).
+ * Arrays: level n at offset n*len (len = nr_fine cells or nr_fine+1 edges). */
+#define RS(n, j) (rg->r_start_coord[(n) * rg->chunk_len + (j)])
+#define RE(n, j) (rg->r_end_coord[(n) * rg->chunk_len + (j)])
+
+static double mc_slope(const double* c, int r) {
+    /* MaestroBaseStateGeometry.cpp:281-291: limited slope of the coarse cell r */
+    double del = 0.5 * (c[r + 1] - c[r - 1]);
+    double dpls = 2.0 * (c[r + 1] - c[r]);
+    double dmn = 2.0 * (c[r] - c[r - 1]);
+    double slim = dmin(fabs(dpls), fabs(dmn));
+    slim = dpls * dmn > 0.0 ? slim : 0.0;
+    return copysign(1.0, del) * dmin(slim, fabs(del));
+}
+
+static void restrict_base(const MxRadialGeom* rg, double* s0, int len, int cc) {
+    for (int n = rg->finest_radial_level; n >= 1; --n)
+        for (int i = 1; i <= rg->numdisjointchunks[n]; ++i) {
+            double *f = s0 + (long)n * len, *c = s0 + (long)(n - 1) * len;
+            if (cc) {
+                for (int j = RS(n, i); j < RE(n, i); j += 2) c[j / 2] = 0.5 * (f[j] + f[j + 1]);
+            } else {
+                for (int j = RS(n, i); j <= RE(n, i) + 1; j += 2) c[j / 2] = f[j];
+            }
+        }
+}
+
+static void fill_ghost_base(const MxRadialGeom* rg, double* s0, int len, int cc) {
+    for (int n = rg->finest_radial_level; n >= 1; --n)
+        for (int i = 1; i <= rg->numdisjointchunks[n]; ++i) {
+            const int lo = RS(n, i), hi = RE(n, i);
+            double *f = s0 + (long)n * len, *c = s0 + (long)(n - 1) * len;
+            if (cc) {
+                if (lo != 0) {
+                    int rc = lo / 2 - 1;
+                    double sl = mc_slope(c, rc);
+                    f[lo - 1] = c[rc] + 0.25 * sl;
+                    f[lo - 2] = c[rc] - 0.25 * sl;
+                    rc = lo / 2 - 2;
+                    sl = mc_slope(c, rc);
+                    f[lo - 3] = c[rc] + 0.25 * sl;
+                    f[lo - 4] = c[rc] - 0.25 * sl;
+                }
+                if (hi != rg->nr[n] - 1) {
+                    int rc = (hi + 1) / 2;
+                    double sl = mc_slope(c, rc);
+                    f[hi + 1] = c[rc] - 0.25 * sl;
+                    f[hi + 2] = c[rc] + 0.25 * sl;
+                    rc = (hi + 1) / 2 + 1;
+                    sl = mc_slope(c, rc);
+                    f[hi + 3] = c[rc] - 0.25 * sl;
+                    f[hi + 4] = c[rc] + 0.25 * sl;
+                }
+            } else {
+                if (lo != 0) {
+                    f[lo - 1] = -f[lo + 1] / 3.0 + f[lo] + c[lo / 2 - 1] / 3.0;
+                    f[lo - 2] = c[(lo - 2) / 2];
+                }
+                if (hi + 1 != rg->nr[n]) {
+                    f[hi + 2] = -f[hi] / 3.0 + f[hi + 1] + c[(hi + 3) / 2] / 3.0;
+                    f[hi + 3] = c[(hi + 3) / 2];
+                }
+            }
+        }
+}
+
+int orc_make_w0_planar_ml(const MxW0Params* p, const MxRadialGeom* rg, const double* w0_old,
+                          const double* Sbar, const double* p0_old, const double* p0_new,
+                          const double* g1o, const double* g1n, const double* pmp,
+                          const double* etarho_cc, double* w0, double* w0_force, double* p0bdot) {
+    const int nrf = rg->nr_fine, nlev = rg->max_radial_level + 1;
+    const int lc = nrf, le = nrf + 1;
+    double* psi = (double*)calloc((size_t)nrf + 1, sizeof(double));
+    double* int1 = (double*)calloc((size_t)nrf + 2, sizeof(double));
+    for (long q = 0; q < (long)nlev * le; ++q) w0[q] = 0.0; /* w0.setVal(0.0), :87 */
+    for (long q = 0; q < (long)nlev * lc; ++q) w0_force[q] = 0.0; /* Makew0: w0_force.setVal(0.), :18 */
+#define W(n, r) w0[(long)(n) * le + (r)]
+#define C(a, n, r) a[(long)(n) * lc + (r)]
+    for (int n = 0; n <= rg->max_radial_level; ++n) {
+        for (int r = 0; r < nrf; ++r) psi[r] = 0.0;
+        const int cut = rg->base_cutoff_density_coord[n];
+        const double dr = rg->dr[n];
+        for (int j = 1; j <= rg->numdisjointchunks[n]; ++j) {
+            if (n == 0) {
+                W(0, 0) = 0.0;
+                int1[0] = 0.0;
+            } else {
+                W(n, RS(n, j)) = W(n - 1, RS(n, j) / 2); /* :125-127 */
+            }
+            for (int r = RS(n, j); r <= RE(n, j); ++r)
+                if (r < cut) psi[r] = C(etarho_cc, n, r) * fabs(p->grav_const);
+            for (int r = RS(n, j) + 1; r <= RE(n, j) + 1; ++r) {
+                double gavg = (C(g1o, n, r - 1) + C(g1n, n, r - 1)) * (C(p0_old, n, r - 1) + C(p0_new, n, r - 1)) / 4.0;
+                double dchi = 0.0;
+                if (r < cut) {
+                    if (p->is_predictor)
+                        dchi = p->dpdt_factor * C(pmp, n, r - 1) / (C(g1o, n, r - 1) * C(p0_old, n, r - 1) * p->dt);
+                    else
+                        dchi += p->dpdt_factor * C(pmp, n, r - 1) / (C(g1n, n, r - 1) * C(p0_new, n, r - 1) * p->dt);
+                }
+                if (n == 0) int1[r] = int1[r - 1] + (1.0 / gavg) * dr;
+                W(n, r) = W(n, r - 1) + C(Sbar, n, r - 1) * dr - psi[r - 1] / gavg * dr - dchi * dr;
+            }
+            if (n == 0 && p->add_pb) { /* :175-184 */
+                const int k = RE(n, j) + 1;
+                const double pb = W(n, k) / int1[k];
+                if (p0bdot) *p0bdot = pb;
+                for (int r = RS(n, j) + 1; r <= RE(n, j) + 1; ++r) W(n, r) -= pb * int1[r];
+            }
+            if (n > 0) { /* :185-213 */
+                const double offset = W(n, RE(n, j) + 1) - W(n - 1, (RE(n, j) + 1) / 2);
+                for (int i = n - 1; i >= 0; --i) {
+                    const int refrat = 1 << (n - i);
+                    /* QUIRK :196: the restriction writes level n, not level i */
+                    for (int r = RS(n, j); r <= RE(n, j) + 1; ++r)
+                        if (r % refrat == 0) W(n, r / refrat) = W(n, r);
+                    for (int r = (RE(n, j) + 1) / refrat + 1; r <= rg->nr[i]; ++r) W(i, r) += offset;
+                }
+            }
+        }
+    }
+    for (int n = 1; n <= rg->max_radial_level; ++n) /* :216-236 */
+        for (int j = 1; j <= rg->numdisjointchunks[n]; ++j) {
+            const int lo = RE(n, j) + 2;
+            const int hi = j == rg->numdisjointchunks[n] ? rg->nr[n] : RS(n, j + 1) - 1;
+            for (int r = lo; r <= hi; ++r) W(n, r) = 0.0;
+        }
+    restrict_base(rg, w0, le, 0);
+    fill_ghost_base(rg, w0, le, 0);
+    const double dt_avg = 0.5 * (p->dt_in + p->dtold_in);
+    for (int n = 0; n <= rg->max_radial_level; ++n)
+        for (int j = 1; j <= rg->numdisjointchunks[n]; ++j)
+            for (int r = RS(n, j); r <= RE(n, j); ++r) { /* :241-268 */
+                const double* wo = w0_old + (long)n * le;
+                double w0_old_cen = 0.5 * (wo[r] + wo[r + 1]);
+                double w0_new_cen = 0.5 * (W(n, r) + W(n, r + 1));
+                double w0_avg = 0.5 * (p->dt_in * w0_old_cen + p->dtold_in * w0_new_cen) / dt_avg;
+                double div_avg = 0.5 * (p->dt_in * (wo[r + 1] - wo[r]) + p->dtold_in * (W(n, r + 1) - W(n, r))) / dt_avg;
+                w0_force[(long)n * lc + r] = (w0_new_cen - w0_old_cen) / dt_avg + w0_avg * div_avg / rg->dr[n];
+            }
+    restrict_base(rg, w0_force, lc, 1);
+    fill_ghost_base(rg, w0_force, lc, 1);
+#undef W
+#undef C
+    free(psi);
+    free(int1);
+    return 0;
+}
+#undef RS
+#undef RE

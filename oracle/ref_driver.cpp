@@ -33,6 +33,7 @@ Real base_cutoff_density = -1.0, dpdt_factor = 0.0, planar_invsq_mass = 0.0,
 bool do_sponge = false, do_eos_h_above_cutoff = true;
 int s0_interp_type = 3, w0_interp_type = 2, s0mac_interp_type = 1, w0mac_interp_type = 1;
 Real buoyancy_cutoff_factor = 5.0;
+Real anelastic_cutoff_density = -1.0, burning_cutoff_density_lo = -1.0, burning_cutoff_density_hi = 1.e100;
 }  // namespace maestro
 int Rho = 0, RhoH = 1, Temp = 2, Pi = 3, FirstSpec = 4, NumSpec = 3, Nscal = 7;
 
@@ -42,11 +43,20 @@ IntVect Maestro::nodal_flag(1, 1);
 #else
 IntVect Maestro::nodal_flag(1, 1, 1);
 #endif
-// defined in Source/MaestroBaseStateGeometry.cpp, only reached with use_exact_base_state
+#if (AMREX_SPACEDIM == 2)
+// Source/MaestroBaseStateGeometry.cpp defines it for 3-D only; MakeCCtoRadii is never called in 2-D
 void Maestro::InitBaseStateMapSphr(const int, const MFIter&, const GpuArray<Real, AMREX_SPACEDIM>,
                                    const GpuArray<Real, AMREX_SPACEDIM>) {
-    Abort("ref_driver: InitBaseStateMapSphr is not on the tested path");
+    Abort("ref_driver: InitBaseStateMapSphr is 3-D only");
 }
+#endif
+#else
+// the overlay test library: one radial level, where the reference's RestrictBase / FillGhostBase
+// (loops over radial levels >= 1) do nothing
+void Maestro::RestrictBase(BaseState<Real>&, const bool) const {}
+void Maestro::RestrictBase(const BaseStateArray<Real>&, const bool) const {}
+void Maestro::FillGhostBase(BaseState<Real>&, const bool) const {}
+void Maestro::FillGhostBase(const BaseStateArray<Real>&, const bool) const {}
 #endif
 #if (AMREX_SPACEDIM == 2)
 IntVect Maestro::nodal_flag_x(1, 0);
@@ -660,5 +670,65 @@ int DRV(update_vel)(const MxGeom* g, const MxFab* uold, const MxFab* unew, const
     return 0;
 }
 #endif  // !DRV_OVERLAY
+
+#ifndef DRV_OVERLAY
+// Maestro::Makew0 -> Makew0Planar with a MULTILEVEL base state (Source/MaestroMakew0.cpp:60-272)
+// incl. the reference's own RestrictBase / FillGhostBase (MaestroBaseStateGeometry.cpp)
+int DRV(make_w0_planar_ml)(const MxW0Params* p, const MxRadialGeom* rg, const double* w0_old,
+                          const double* Sbar, const double* p0_old, const double* p0_new,
+                          const double* g1o, const double* g1n, const double* pmp,
+                          const double* etarho_cc, double* w0, double* w0_force, double* p0bdot) {
+    Maestro m;
+    const int nlev = rg->max_radial_level + 1, nf = rg->finest_radial_level + 1, nrf = rg->nr_fine;
+    auto& bg = m.base_geom;
+    bg.max_radial_level = rg->max_radial_level;
+    bg.finest_radial_level = rg->finest_radial_level;
+    bg.nr_fine = nrf;
+    bg.dr_fine = rg->dr[rg->max_radial_level];
+    bg.nr_irreg = 0;
+    bg.nr.init(const_cast<int*>(rg->nr), nlev, 1, 1);
+    bg.dr.init(const_cast<double*>(rg->dr), nlev, 1, 1);
+    bg.base_cutoff_density_coord.init(const_cast<int*>(rg->base_cutoff_density_coord), nlev, 1, 1);
+    bg.numdisjointchunks.init(const_cast<int*>(rg->numdisjointchunks), nf, 1, 1);
+    bg.r_start_coord.init(const_cast<int*>(rg->r_start_coord), nf, rg->chunk_len, 1);
+    bg.r_end_coord.init(const_cast<int*>(rg->r_end_coord), nf, rg->chunk_len, 1);
+    maestro::spherical = false;
+    maestro::use_exact_base_state = false;
+    maestro::do_planar_invsq_grav = false;
+    maestro::do_2d_planar_octant = false;
+    maestro::maestro_verbose = 0;
+    maestro::add_pb = p->add_pb != 0;
+    maestro::grav_const = p->grav_const;
+    maestro::dpdt_factor = p->dpdt_factor;
+    maestro::base_cutoff_density = p->base_cutoff_density;
+    m.dt = p->dt;
+    auto fill = [&](BaseState<Real>& b, const double* src, int len) {
+        b.define(nlev, len, 1);
+        auto a = b.array();
+        for (int i = 0; i < nlev * len; ++i) a(i) = src ? src[i] : 0.0;
+    };
+    BaseState<Real> b_w0o, b_force, b_S, b_r0, b_p0o, b_p0n, b_g1o, b_g1n, b_pmp;
+    fill(b_w0o, w0_old, nrf + 1);
+    fill(b_force, nullptr, nrf);
+    fill(b_S, Sbar, nrf);
+    fill(b_r0, nullptr, nrf);
+    fill(b_p0o, p0_old, nrf);
+    fill(b_p0n, p0_new, nrf);
+    fill(b_g1o, g1o, nrf);
+    fill(b_g1n, g1n, nrf);
+    fill(b_pmp, pmp, nrf);
+    fill(m.w0, nullptr, nrf + 1);
+    fill(m.etarho_cc, etarho_cc, nrf);
+    fill(m.etarho_ec, nullptr, nrf + 1);
+    m.Makew0(b_w0o, b_force, b_S, b_r0, b_r0, b_p0o, b_p0n, b_g1o, b_g1n, b_pmp, p->dt_in, p->dtold_in,
+             p->is_predictor != 0);
+    auto wa = m.w0.array();
+    auto fa = b_force.array();
+    for (int i = 0; i < nlev * (nrf + 1); ++i) w0[i] = wa(i);
+    for (int i = 0; i < nlev * nrf; ++i) w0_force[i] = fa(i);
+    if (p0bdot && p->add_pb) *p0bdot = m.p0bdot;
+    return 0;
+}
+#endif
 
 }  // extern "C"
