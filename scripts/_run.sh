@@ -1,15 +1,7 @@
-O=gpurun_out/final; mkdir -p $O
-MXADV_FCOMPARE_OUT=$O/fcompare timeout -k 10 2400 python -m pytest tests -q -m gpu 2>&1 | tail -6 | tee $O/pytest_gpu.log
-timeout -k 10 900 python bench.py --steps 5 --warmup 3 > $O/bench_512.json 2> $O/bench_512.err; tail -c 400 $O/bench_512.json
-timeout -k 10 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err; tail -c 300 $O/bench_reference_arm.json
-timeout -k 10 600 python bench.py --size 256 --steps 5 --warmup 3 --no-cpu > $O/bench_256.json 2> $O/bench_256.err
-# launch list of the bench command (per-launch times are cold-cache / serialised: shares only)
-timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_n256.csv python bench.py --size 256 --steps 2 --warmup 3 --no-cpu --no-e2e > $O/launches.log 2>&1
-# full capture of the dominant kernel (density launch)
-timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:k_stream4 -s 6 -c 1 -o $O/prof_k_stream4_n256 -f python bench.py --size 256 --steps 1 --warmup 3 --no-cpu --no-e2e > $O/ncu_full.log 2>&1; tail -2 $O/ncu_full.log
-# DRAM traffic of one density launch at 512^3
-timeout -k 10 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_stream4 -s 6 -c 2 --csv --log-file $O/traffic_n512.csv python bench.py --size 512 --steps 1 --warmup 3 --no-cpu --no-e2e > $O/traffic.log 2>&1; tail -3 $O/traffic_n512.csv | cut -c1-200
-# tolerance-mode A/B
+O=gpurun_out/x1; mkdir -p $O
+# tolerance-mode A/B errors (the earlier run lacked the import path)
 timeout -k 10 300 python tools/fmad_err.py dump $O/strict.npz; MXADV_LIB=exp/fmad/libmxadv.so timeout -k 10 300 python tools/fmad_err.py dump $O/fmad.npz; python tools/fmad_err.py compare $O/strict.npz $O/fmad.npz | tee $O/fmad_err.txt; rm -f $O/strict.npz $O/fmad.npz
-for s in 256 512; do MXADV_LIB=exp/fmad/libmxadv.so timeout -k 10 600 python bench.py --size $s --steps 5 --warmup 3 --no-cpu --no-e2e > $O/bench_${s}_fmad.json 2>/dev/null; python -c "
-import json; d=json.loads(open('$O/bench_${s}_fmad.json').read().strip().splitlines()[-1]); print('fmad', $s, 'ms/launch', d['roofline']['ms_per_launch'], 'frac', d['roofline']['frac'])"; done
+# pair-sync variant: parity first
+MXADV_LIB=exp/pair/libmxadv.so timeout -k 10 600 python -m pytest tests/test_gpu_tma.py tests/test_gpu_fullsize.py -x -q -m gpu -k "not 512" 2>&1 | tail -5 | tee $O/pytest_pair.log
+TAG=x1 scripts/gpu.sh ab 256 tree pair fakein gy20 gy18
+TAG=x1 scripts/gpu.sh ab 512 tree pair
