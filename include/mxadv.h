@@ -487,6 +487,46 @@ int mx_update_vel(const MxGeom* geom, const MxFab* uold, const MxFab* unew, cons
                   const MxFab* w0_cart, const MxFab* w0mac, double dt, int do_sponge,
                   int spherical, void* stream);
 
+/* ---- MAC-velocity predictor ----------------------------------
+ * Runtime parameters of Maestro::MakeUtrans / Maestro::VelPred: dt and rel_eps are Maestro
+ * members (Source/Maestro.H:1873,1974), ppm_type / slope_order / ppm_trace_forces / spherical
+ * come from Source/param/_cpp_parameters, phys_bc is Maestro::phys_bc (Source/Maestro.H:1917,
+ * amrex::PhysBCType codes: 0 interior, 1 inflow, 2 outflow, 3 symmetry, 4 slipwall,
+ * 5 noslipwall), bc is Maestro::bcs_u. */
+typedef struct MxVelPredParams {
+    double dt;
+    double rel_eps;
+    int ppm_type;         /* 0 (slopes), 1, 2 */
+    int slope_order;      /* 0, 2, 4 (used when ppm_type == 0) */
+    int ppm_trace_forces; /* VelPred only; 3-D only (the reference's 2-D branch reads Ipfy / Imfy
+                             without ever filling them, MaestroVelPred.cpp:134-139) */
+    int spherical;
+    int phys_bc_lo[3];
+    int phys_bc_hi[3];
+    const int* bc; /* HOST pointer, dim x 6: {lo_x,lo_y,lo_z,hi_x,hi_y,hi_z} per velocity component */
+} MxVelPredParams;
+
+/* Replaces Maestro::MakeUtrans (Source/MaestroMakeUtrans.cpp:6-648, decl Maestro.H:1172-1177)
+ * for one box: the transverse velocities on the faces of the valid box from Slopex/y/z or
+ * PPM(is_umac = false) of the normal component, phys_bc, and the Riemann problem with the full
+ * velocity (w0mac when spherical, w0_cart's last component in the last direction otherwise).
+ * utilde: dim components, >= 3 ghost cells (4 if ppm_type == 2); ufull: dim components, >= 1
+ * ghost cell; utrans[d]: face-centred in d, written on the faces of the valid box; w0_cart
+ * (planar; one ghost cell in the last direction) or w0mac[3] (spherical).  FillBoundary /
+ * FillUmacGhost / AverageDownFaces / FillPatchUedge (:630-647) stay with the caller. */
+int mx_make_utrans(const MxGeom* geom, const MxFab* utilde, const MxFab* ufull,
+                   const MxFab* utrans /*[dim]*/, const MxFab* w0_cart, const MxFab* w0mac,
+                   const MxVelPredParams* par, void* stream);
+
+/* Replaces Maestro::VelPred (Source/MaestroVelPred.cpp:5-1917, decl Maestro.H:1711-1842) for one
+ * box, including VelPredInterface, VelPredTransverse (3-D) and VelPredVelocities.  utrans[d]
+ * (already containing w0, one ghost cell) is read; umac[d] is written on the faces of the valid
+ * box; force: dim components, >= 1 ghost cell (utilde's ghost cells if ppm_trace_forces).
+ * AverageDownFaces (:293) stays with the caller. */
+int mx_vel_pred(const MxGeom* geom, const MxFab* utilde, const MxFab* ufull,
+                const MxFab* utrans /*[dim]*/, const MxFab* umac /*[dim]*/, const MxFab* w0mac,
+                const MxFab* w0_cart, const MxFab* force, const MxVelPredParams* par, void* stream);
+
 /* ---- fused advances (the update that follows the fluxes) -------
  * mx_density_advance = mx_density_edge_flux + the part of DensityAdvance that follows it
  * (Source/MaestroDensityAdvance.cpp:144-258): rho' -> rho (PutInPertForm, flag false; only for

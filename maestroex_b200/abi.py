@@ -57,6 +57,20 @@ class MxEdgeParams(C.Structure):
     ]
 
 
+class MxVelPredParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("rel_eps", C.c_double),
+        ("ppm_type", C.c_int),
+        ("slope_order", C.c_int),
+        ("ppm_trace_forces", C.c_int),
+        ("spherical", C.c_int),
+        ("phys_bc_lo", C.c_int * 3),
+        ("phys_bc_hi", C.c_int * 3),
+        ("bc", c_int_p),
+    ]
+
+
 class MxFluxParams(C.Structure):
     _fields_ = [
         ("species_pred_type", C.c_int),
@@ -238,6 +252,42 @@ class EdgeParams:
         assert bc.ndim == 2 and bc.shape[1] == 6
         self._keep.append(bc)
         p.nbccomp = bc.shape[0]
+        p.bc = bc.ctypes.data_as(c_int_p)
+        return p
+
+
+# amrex::PhysBCType (AMReX_BC_TYPES.H:61-64)
+PHYS_INTERIOR, PHYS_INFLOW, PHYS_OUTFLOW, PHYS_SYMMETRY, PHYS_SLIPWALL, PHYS_NOSLIPWALL = range(6)
+
+
+@dataclass
+class VelPredParams:
+    """Runtime parameters of Maestro::MakeUtrans / VelPred (MxVelPredParams)."""
+    dt: float
+    rel_eps: float
+    ppm_type: int = 1
+    slope_order: int = 4
+    ppm_trace_forces: int = 0
+    spherical: int = 0
+    phys_bc_lo: tuple = (0, 0, 0)
+    phys_bc_hi: tuple = (0, 0, 0)
+    bc: Optional[np.ndarray] = None  # (dim, 6) int32: bcs_u, lo_x,lo_y,lo_z,hi_x,hi_y,hi_z
+    _keep: list = field(default_factory=list, repr=False)
+
+    def c(self) -> MxVelPredParams:
+        p = MxVelPredParams()
+        p.dt = self.dt
+        p.rel_eps = self.rel_eps
+        p.ppm_type = self.ppm_type
+        p.slope_order = self.slope_order
+        p.ppm_trace_forces = self.ppm_trace_forces
+        p.spherical = self.spherical
+        for d in range(3):
+            p.phys_bc_lo[d] = self.phys_bc_lo[d] if d < len(self.phys_bc_lo) else 0
+            p.phys_bc_hi[d] = self.phys_bc_hi[d] if d < len(self.phys_bc_hi) else 0
+        bc = np.ascontiguousarray(self.bc, dtype=np.int32)
+        assert bc.ndim == 2 and bc.shape[1] == 6
+        self._keep.append(bc)
         p.bc = bc.ctypes.data_as(c_int_p)
         return p
 

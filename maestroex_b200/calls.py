@@ -239,3 +239,21 @@ class Calls:
                                     self._fab(w0_cart), self._faces(w0mac), C.c_double(dt),
                                     do_sponge, spherical, *self._tail(stream))
         self._check(rc, "update_vel")
+
+    # -- Maestro::MakeUtrans (Source/MaestroMakeUtrans.cpp:6-648) --------------------------
+    def make_utrans(self, geom: Geom, utilde: Fab, ufull: Fab, utrans, w0_cart: Fab, w0mac, par,
+                    stream: int = 0):
+        g, ut, uf, p = geom.c(), utilde.c(), ufull.c(), par.c()
+        rc = self._fn("make_utrans")(C.byref(g), C.byref(ut), C.byref(uf), self._faces(utrans),
+                                     self._fab(w0_cart), self._faces(w0mac), C.byref(p),
+                                     *self._tail(stream))
+        self._check(rc, "make_utrans")
+
+    # -- Maestro::VelPred (Source/MaestroVelPred.cpp:5-1917) --------------------------------
+    def vel_pred(self, geom: Geom, utilde: Fab, ufull: Fab, utrans, umac, w0mac, w0_cart: Fab,
+                 force: Fab, par, stream: int = 0):
+        g, ut, uf, fo, p = geom.c(), utilde.c(), ufull.c(), force.c(), par.c()
+        rc = self._fn("vel_pred")(C.byref(g), C.byref(ut), C.byref(uf), self._faces(utrans),
+                                  self._faces(umac), self._faces(w0mac), self._fab(w0_cart),
+                                  C.byref(fo), C.byref(p), *self._tail(stream))
+        self._check(rc, "vel_pred")

@@ -18,6 +18,7 @@
 #include "mx_w0.h"
 #include "mx_update.h"
 #include "mx_cart.h"
+#include "mx_velpred.h"
 #include "mx_fused.h"
 #include "mx_staged.h"
 
@@ -1593,6 +1594,124 @@ int mx_update_vel(const MxGeom* geom, const MxFab* uold, const MxFab* unew, cons
         MX_TRY(S.fab(w0_cart, &w0c, last, 1, true, false));
     }
     cart_update_vel(make_kgeom(geom), uo, un, um, ue, fo, sp, w0c, wm, dt, do_sponge, spherical, S.stream());
+    return S.finish();
+}
+
+
+// ---- MakeUtrans / VelPred -----------------------------------------------------------------
+static int vel_params(const MxGeom* g, const MxVelPredParams* p, KVel* e) {
+    if (p == nullptr || p->bc == nullptr) return fail(MX_ERR_INVALID, "null velocity-predictor parameters");
+    if (p->ppm_type < 0 || p->ppm_type > 2)
+        return fail(MX_ERR_UNSUPPORTED, "ppm_type %d (reference supports 0, 1, 2)", p->ppm_type);
+    if (p->ppm_type == 0 && p->slope_order != 0 && p->slope_order != 2 && p->slope_order != 4)
+        return fail(MX_ERR_UNSUPPORTED, "slope_order %d (reference supports 0, 2, 4)", p->slope_order);
+    if (p->spherical && g->dim != 3) return fail(MX_ERR_INVALID, "spherical is 3-D only");
+    memset(e, 0, sizeof(*e));
+    e->dt = p->dt;
+    e->eps = p->rel_eps;
+    e->ppm_type = p->ppm_type;
+    e->slope_order = p->slope_order;
+    e->trace = p->ppm_trace_forces != 0;
+    e->spherical = p->spherical != 0;
+    for (int d = 0; d < g->dim; ++d) {
+        e->pbc_lo[d] = p->phys_bc_lo[d];
+        e->pbc_hi[d] = p->phys_bc_hi[d];
+        if (e->pbc_lo[d] < 0 || e->pbc_lo[d] > 5 || e->pbc_hi[d] < 0 || e->pbc_hi[d] > 5)
+            return fail(MX_ERR_INVALID, "invalid boundary type");  // the reference's amrex::Error
+        for (int n = 0; n < g->dim; ++n) {
+            e->bclo[n][d] = p->bc[n * 6 + d];
+            e->bchi[n][d] = p->bc[n * 6 + 3 + d];
+        }
+    }
+    return MX_OK;
+}
+
+// w0_cart (planar: last component, one ghost cell in the last direction) or w0mac (spherical)
+static int vel_w0(Session& S, const MxGeom* geom, int spherical, const MxFab* w0_cart,
+                  const MxFab* w0mac, DFab* w0c, DFab* wm) {
+    const int dim = geom->dim;
+    memset(w0c, 0, sizeof(*w0c));
+    if (spherical) {
+        if (!w0mac) return fail(MX_ERR_INVALID, "spherical: w0mac is required");
+        for (int d = 0; d < dim; ++d) {
+            MX_TRY(check_cover(geom, &w0mac[d], 0, d, "w0mac"));
+            MX_TRY(S.fab(&w0mac[d], &wm[d], 0, 1, true, false));
+        }
+        return MX_OK;
+    }
+    if (!w0_cart) return fail(MX_ERR_INVALID, "planar: w0_cart is required");
+    if (w0_cart->ncomp < dim) return fail(MX_ERR_INVALID, "w0_cart needs dim components");
+    const int last = dim - 1;
+    for (int d = 0; d < dim; ++d) {
+        const int ng = d == last ? 1 : 0;
+        if (w0_cart->lo[d] > geom->valid_lo[d] || w0_cart->hi[d] < geom->valid_hi[d] + ng)
+            return fail(MX_ERR_INVALID, "w0_cart needs one ghost cell in the last direction");
+    }
+    return S.fab(w0_cart, w0c, last, 1, true, false);
+}
+
+int mx_make_utrans(const MxGeom* geom, const MxFab* utilde, const MxFab* ufull, const MxFab* utrans,
+                   const MxFab* w0_cart, const MxFab* w0mac, const MxVelPredParams* par, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!utilde || !ufull || !utrans) return fail(MX_ERR_INVALID, "null argument");
+    KVel e;
+    MX_TRY(vel_params(geom, par, &e));
+    const int dim = geom->dim;
+    if (utilde->ncomp < dim || ufull->ncomp < dim) return fail(MX_ERR_INVALID, "velocity fabs need dim components");
+    MX_TRY(check_cover(geom, utilde, e.ppm_type == 2 ? 4 : 3, -1, "utilde"));
+    MX_TRY(check_cover(geom, ufull, 1, -1, "ufull"));
+    MX_TRY(require_device());
+    Session S(stream);
+    DFab ut, uf, w0c, wm[3], tr[3];
+    MX_TRY(S.fab(utilde, &ut, 0, dim, true, false));
+    MX_TRY(S.fab(ufull, &uf, 0, dim, true, false));
+    for (int d = 0; d < dim; ++d) {
+        MX_TRY(check_cover(geom, &utrans[d], 0, d, "utrans"));
+        // ghost faces keep the caller's values: read-modify-write unless the fab has none
+        MX_TRY(S.fab(&utrans[d], &tr[d], 0, 1, !exact_face_box(geom, &utrans[d], d), true));
+    }
+    MX_TRY(vel_w0(S, geom, e.spherical, w0_cart, w0mac, &w0c, wm));
+    vel_make_utrans(make_kgeom(geom), e, ut, uf, tr, w0c, e.spherical ? wm : nullptr, S.stream());
+    return S.finish();
+}
+
+int mx_vel_pred(const MxGeom* geom, const MxFab* utilde, const MxFab* ufull, const MxFab* utrans,
+                const MxFab* umac, const MxFab* w0mac, const MxFab* w0_cart, const MxFab* force,
+                const MxVelPredParams* par, void* stream) {
+    MX_TRY(check_geom(geom));
+    if (!utilde || !ufull || !utrans || !umac || !force) return fail(MX_ERR_INVALID, "null argument");
+    KVel e;
+    MX_TRY(vel_params(geom, par, &e));
+    const int dim = geom->dim;
+    if (e.trace && dim == 2)
+        return fail(MX_ERR_UNSUPPORTED,
+                    "VelPred with ppm_trace_forces in 2-D: the reference reads Ipfy / Imfy without "
+                    "filling them (MaestroVelPred.cpp:134-139)");
+    if (e.trace && e.ppm_type == 0)
+        return fail(MX_ERR_UNSUPPORTED, "ppm_trace_forces needs ppm_type 1 or 2");
+    if (utilde->ncomp < dim || ufull->ncomp < dim || force->ncomp < dim)
+        return fail(MX_ERR_INVALID, "velocity fabs need dim components");
+    const int ngs = e.ppm_type == 2 ? 4 : 3;
+    MX_TRY(check_cover(geom, utilde, ngs, -1, "utilde"));
+    MX_TRY(check_cover(geom, ufull, 1, -1, "ufull"));
+    MX_TRY(check_cover(geom, force, e.trace ? ngs : 1, -1, "force"));
+    MX_TRY(require_device());
+    Session S(stream);
+    DFab ut, uf, fo, w0c, wm[3], tr[3], um[3];
+    MX_TRY(S.fab(utilde, &ut, 0, dim, true, false));
+    MX_TRY(S.fab(ufull, &uf, 0, dim, true, false));
+    MX_TRY(S.fab(force, &fo, 0, dim, true, false));
+    for (int d = 0; d < dim; ++d) {
+        MX_TRY(check_cover(geom, &utrans[d], 1, d, "utrans"));
+        MX_TRY(check_cover(geom, &umac[d], 0, d, "umac"));
+        MX_TRY(S.fab(&utrans[d], &tr[d], 0, 1, true, false));
+        MX_TRY(S.fab(&umac[d], &um[d], 0, 1, !exact_face_box(geom, &umac[d], d), true));
+    }
+    MX_TRY(vel_w0(S, geom, e.spherical, w0_cart, w0mac, &w0c, wm));
+    const KGeom kg = make_kgeom(geom);
+    void* ws = nullptr;
+    CUDA_OK(S.alloc(&ws, sizeof(double) * vel_pred_workspace(kg)));
+    vel_pred(kg, e, ut, uf, tr, um, e.spherical ? wm : nullptr, w0c, fo, static_cast<double*>(ws), S.stream());
     return S.finish();
 }
 

@@ -1,0 +1,444 @@
+// mx_velpred.cu — the MAC-velocity predictor either side of the scalar path (SURVEY.md section
+// 8f, rank 4): Maestro::MakeUtrans and Maestro::VelPred for one box, 2-D and 3-D, ppm_type 0/1/2,
+// planar and spherical, every phys_bc code.
+//
+//   Source/MaestroMakeUtrans.cpp:6-648     MakeUtrans            -> vel_make_utrans
+//   Source/MaestroVelPred.cpp:5-294        VelPred (driver)      -> vel_pred
+//   :296-542 (2-D) / :735-1128 (3-D)       VelPredInterface      -> interface stage
+//   :1130-1595                             VelPredTransverse     -> transverse stage (3-D)
+//   :544-733 (2-D) / :1597-1917 (3-D)      VelPredVelocities     -> velocity stage
+//
+// Decomposition: the reference builds Ip / Im (or slopes) of every velocity component in every
+// direction as MultiFabs first; here a face forms the parabola (or slope) of its two
+// neighbouring cells on the fly from the shared reconstruction of mx_device.cuh
+// (PPM with is_umac = false: both characteristic integrals use the cell-centred velocity,
+// MaestroPPM.cpp:233-251), so only the interface states (ul, ur, uimh) and the six
+// corner-coupled states go through device workspace.  One thread per zone of the grown box,
+// i fastest; three launches per VelPred call, one per MakeUtrans call.
+//
+// Parity contract as in mx_device.cuh: reference expression trees (association included: the
+// 2-D and 3-D slope extrapolations differ, MaestroVelPred.cpp:336-345 vs :785-796), -fmad=false,
+// IEEE divisions.  Reference quirks that are kept are marked QUIRK.
+#include "mx_common.h"
+#include "mx_device.cuh"
+#include "mx_velpred.h"
+
+using namespace mxd;
+
+namespace {
+
+// amrex::PhysBCType (AMReX_BC_TYPES.H:61-64)
+constexpr int P_INTERIOR = 0, P_INFLOW = 1, P_OUTFLOW = 2, P_SYMMETRY = 3, P_SLIPWALL = 4,
+              P_NOSLIPWALL = 5;
+
+struct Box3 {
+    int lo[3], hi[3];
+};
+
+template <class F>
+__global__ void __launch_bounds__(128) k_vbox(Box3 b, F f) {
+    const int i = b.lo[0] + blockIdx.x * 128 + threadIdx.x;
+    const int j = b.lo[1] + blockIdx.y;
+    const int k = b.lo[2] + blockIdx.z;
+    if (i <= b.hi[0]) f(i, j, k);
+}
+
+template <class F>
+void for_box(const Box3& b, cudaStream_t st, F f) {
+    const int nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return;
+    dim3 grid((nx + 127) / 128, ny, nz);
+    k_vbox<<<grid, 128, 0, st>>>(b, f);
+    mx_count_launch();
+}
+
+// amrex::grow(mfi.tilebox(), 1) in the problem's dimensions
+Box3 grown_box(const KGeom& g) {
+    Box3 b;
+    for (int d = 0; d < 3; ++d) {
+        const int ng = d < g.dim ? 1 : 0;
+        b.lo[d] = g.vlo[d] - ng;
+        b.hi[d] = g.vhi[d] + ng;
+    }
+    return b;
+}
+
+struct I3 {
+    int v[3];
+};
+MXD I3 mk(int i, int j, int k) { return I3{{i, j, k}}; }
+MXD I3 sh(I3 c, int d, int s) {
+    c.v[d] += s;
+    return c;
+}
+MXD double& at(const DFab& f, const I3& c, int n = 0) {
+    return f.p[f.off(c.v[0], c.v[1], c.v[2]) + (long)n * f.sn];
+}
+MXD bool inside(const Box3& b, const I3& c) {
+    return c.v[0] >= b.lo[0] && c.v[0] <= b.hi[0] && c.v[1] >= b.lo[1] && c.v[1] <= b.hi[1] &&
+           c.v[2] >= b.lo[2] && c.v[2] <= b.hi[2];
+}
+
+// workspace arrays over the grown box
+struct WS {
+    double* p;
+    Box3 b;
+    long sy, sz, n;
+    MXD long off(const I3& c) const {
+        return (long)(c.v[0] - b.lo[0]) + (long)(c.v[1] - b.lo[1]) * sy + (long)(c.v[2] - b.lo[2]) * sz;
+    }
+    // ul / ur / uimh of direction d, component c; corner-coupled state of component c on d faces
+    MXD double& ul(int d, int c, const I3& x) const { return p[(0 + d * 3 + c) * n + off(x)]; }
+    MXD double& ur(int d, int c, const I3& x) const { return p[(9 + d * 3 + c) * n + off(x)]; }
+    MXD double& imh(int d, int c, const I3& x) const { return p[(18 + d * 3 + c) * n + off(x)]; }
+    MXD double& tr(int c, int d, const I3& x) const { return p[(27 + c * 3 + d) * n + off(x)]; }
+};
+constexpr int WS_ARRAYS = 36;
+
+WS make_ws(const KGeom& g, double* p) {
+    WS w;
+    w.p = p;
+    w.b = grown_box(g);
+    w.sy = w.b.hi[0] - w.b.lo[0] + 1;
+    w.sz = w.sy * (w.b.hi[1] - w.b.lo[1] + 1);
+    w.n = w.sz * (w.b.hi[2] - w.b.lo[2] + 1);
+    return w;
+}
+
+// Slopex/y/z (ppm_type 0: `ip` is the slope) or PPM with is_umac = false of component n of `s`
+// in direction d at cell c; bcs_u[n] decides the one-sided rows (MaestroSlopes.cpp:17-22,
+// MaestroPPM.cpp:30-31)
+struct RC {
+    double ip, im;
+};
+MXD RC recon(const KGeom& g, const KVel& e, const DFab& s, const DFab& uf, int n, int d, const I3& c) {
+    const long st = d == 0 ? 1 : (d == 1 ? s.sy : s.sz);
+    const double* sp_ = s.comp(n) + s.off(c.v[0], c.v[1], c.v[2]);
+    const bool lobc = e.bclo[n][d] == BC_EXT_DIR || e.bclo[n][d] == BC_HOEXTRAP;
+    const bool hibc = e.bchi[n][d] == BC_EXT_DIR || e.bchi[n][d] == BC_HOEXTRAP;
+    double S[7];
+    S[0] = S[6] = 0.0;
+#pragma unroll
+    for (int q = -2; q <= 2; ++q) S[q + 3] = sp_[q * st];
+    RC r;
+    if (e.ppm_type == 0) {
+        r.ip = slope_any(e.slope_order, S + 1, c.v[d], g.dlo[d], g.dhi[d], lobc, hibc, d == 0);
+        r.im = 0.0;
+        return r;
+    }
+    double sm, sp;
+    if (e.ppm_type == 1) {
+        ppm1_parabola<true>(S, c.v[d], g.dlo[d], g.dhi[d], lobc, hibc, sm, sp);
+    } else {
+        S[0] = sp_[-3 * st];
+        S[6] = sp_[3 * st];
+        ppm2_parabola<true>(S, c.v[d], g.dlo[d], g.dhi[d], lobc, hibc, d == 0, sm, sp);
+    }
+    const double u = at(uf, c, d);
+    const double s0 = S[3];
+    const double s6 = 6.0 * s0 - 3.0 * (sm + sp);
+    const double sig = fabs(u) * e.dt / g.dx[d];
+    r.ip = ppm_Ip(sm, sp, s0, s6, u, sig, e.eps);
+    r.im = ppm_Im(sm, sp, s0, s6, u, sig, e.eps);
+    return r;
+}
+
+// the w0 term of the Riemann problems: w0mac on spherical grids, w0_cart's last component in
+// the last direction of planar ones, nothing otherwise (MaestroVelPred.cpp:1651-1667, :1860-1884)
+MXD double w0_term(const KGeom& g, const KVel& e, const DFab* w0mac, const DFab& w0c, int d, const I3& f) {
+    if (e.spherical) return at(w0mac[d], f);
+    if (d == g.dim - 1) return at(w0c, f, g.dim - 1);
+    return 0.0;
+}
+
+// "solve Riemann problem using full velocity"
+MXD double riemann_full(double l, double r, double w, double eps) {
+    const bool test = (l + w <= 0.0 && r + w >= 0.0) || (fabs(l + r + 2.0 * w) < eps);
+    const double v = 0.5 * (l + r) + w > 0.0 ? l : r;
+    return test ? 0.0 : v;
+}
+
+// "upwind using full velocity": trans > 0 ? l : r, average where |trans| < rel_eps
+MXD double upwind_trans(double t, double l, double r, double eps) {
+    const double v = t > 0.0 ? l : r;
+    return fabs(t) < eps ? 0.5 * (l + r) : v;
+}
+
+}  // namespace
+
+size_t vel_pred_workspace(const KGeom& g) {
+    const WS w = make_ws(g, nullptr);
+    return (size_t)w.n * WS_ARRAYS;
+}
+
+// ---- Maestro::MakeUtrans -------------------------------------------------------------------
+void vel_make_utrans(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
+                     const DFab* utrans, const DFab& w0c, const DFab* w0mac_in, cudaStream_t st) {
+    DFab wm[3];
+    for (int d = 0; d < 3; ++d) wm[d] = (e.spherical && w0mac_in) ? w0mac_in[d] : w0c;
+    const DFab wm0 = wm[0], wm1 = wm[1], wm2 = wm[2];
+    for (int d = 0; d < g.dim; ++d) {
+        Box3 fb;
+        for (int q = 0; q < 3; ++q) {
+            fb.lo[q] = g.vlo[q];
+            fb.hi[q] = g.vhi[q] + (q == d ? 1 : 0);
+        }
+        const DFab out = utrans[d];
+        for_box(fb, st, [=] __device__(int i, int j, int k) {
+            const DFab wmac[3] = {wm0, wm1, wm2};
+            const I3 f = mk(i, j, k), cl = sh(f, d, -1);
+            const double dt2 = 0.5 * e.dt;
+            double l, r;
+            const RC L = recon(g, e, utilde, ufull, d, d, cl), R = recon(g, e, utilde, ufull, d, d, f);
+            if (e.ppm_type == 0) {
+                // MaestroMakeUtrans.cpp:94-103
+                l = at(utilde, cl, d) + (0.5 - (dt2 / g.dx[d]) * dmax_(0.0, at(ufull, cl, d))) * L.ip;
+                r = at(utilde, f, d) - (0.5 + (dt2 / g.dx[d]) * dmin_(0.0, at(ufull, f, d))) * R.ip;
+            } else {
+                l = L.ip;
+                r = R.im;
+            }
+            const int I = f.v[d];
+            if (I == g.dlo[d]) {
+                const int bc = e.pbc_lo[d];
+                if (bc == P_INFLOW) {
+                    l = r = at(utilde, cl, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    // QUIRK: the 2-D y sweep zeroes only the right state (:220-221)
+                    if (!(g.dim == 2 && d == 1)) l = 0.0;
+                    r = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    l = dmin_(r, 0.0);
+                    r = l;
+                }
+            } else if (I == g.dhi[d] + 1) {
+                const int bc = e.pbc_hi[d];
+                if (bc == P_INFLOW) {
+                    // QUIRK: 3-D reads one cell further out (:350-351, :466-467, :581-582)
+                    const I3 src = g.dim == 3 ? sh(f, d, 1) : f;
+                    l = r = at(utilde, src, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    l = 0.0;
+                    r = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    l = dmax_(l, 0.0);
+                    r = l;
+                }
+            }
+            at(out, f) = riemann_full(l, r, w0_term(g, e, wmac, w0c, d, f), e.eps);
+        });
+    }
+}
+
+// ---- Maestro::VelPred ------------------------------------------------------------------------
+void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
+              const DFab* utrans_in, const DFab* umac_out, const DFab* w0mac_in, const DFab& w0c,
+              const DFab& force, double* wsp, cudaStream_t st) {
+    const WS W = make_ws(g, wsp);
+    const Box3 obx = W.b;
+    const int dim = g.dim;
+    const DFab ut0 = utrans_in[0], ut1 = utrans_in[1], ut2 = dim == 3 ? utrans_in[2] : utrans_in[1];
+    const DFab um0 = umac_out[0], um1 = umac_out[1], um2 = dim == 3 ? umac_out[2] : umac_out[1];
+    DFab wm[3];
+    for (int d = 0; d < 3; ++d) wm[d] = (e.spherical && w0mac_in) ? w0mac_in[d] : w0c;
+    const DFab wm0 = wm[0], wm1 = wm[1], wm2 = wm[2];
+    Box3 vb;
+    for (int q = 0; q < 3; ++q) {
+        vb.lo[q] = g.vlo[q];
+        vb.hi[q] = g.vhi[q];
+    }
+
+    // ---- VelPredInterface: ul / ur of every component on the faces of mxbx / mybx / mzbx
+    // (obx with the low side of the normal direction pulled in), BCs, transverse uimh --------
+    for_box(obx, st, [=] __device__(int i, int j, int k) {
+        const DFab utr[3] = {ut0, ut1, ut2};
+        const I3 f = mk(i, j, k);
+        const double dt2 = 0.5 * e.dt;
+        for (int d = 0; d < dim; ++d) {
+            if (f.v[d] < obx.lo[d] + 1) continue;
+            const I3 cl = sh(f, d, -1);
+            const double h = g.dx[d];
+            double ul[3], ur[3];
+            if (e.ppm_type == 0) {
+                const double uL = dmax_(0.0, at(ufull, cl, d)), uR = dmin_(0.0, at(ufull, f, d));
+                // 3-D: :785-796; 2-D association differs: :336-345
+                const double fl = dim == 3 ? 0.5 - dt2 * uL / h : 0.5 - (dt2 / h) * uL;
+                const double fr = dim == 3 ? 0.5 + dt2 * uR / h : 0.5 + (dt2 / h) * uR;
+                for (int n = 0; n < dim; ++n) {
+                    ul[n] = at(utilde, cl, n) + fl * recon(g, e, utilde, ufull, n, d, cl).ip;
+                    ur[n] = at(utilde, f, n) - fr * recon(g, e, utilde, ufull, n, d, f).ip;
+                }
+            } else {
+                for (int n = 0; n < dim; ++n) {
+                    ul[n] = recon(g, e, utilde, ufull, n, d, cl).ip;
+                    ur[n] = recon(g, e, utilde, ufull, n, d, f).im;
+                }
+            }
+            const int I = f.v[d];
+            if (I == g.dlo[d]) {
+                const int bc = e.pbc_lo[d];
+                if (bc == P_INFLOW) {
+                    for (int n = 0; n < dim; ++n) ul[n] = ur[n] = at(utilde, cl, n);
+                } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
+                    for (int n = 0; n < dim; ++n) {
+                        if (n == d) {
+                            ul[n] = 0.0;
+                            ur[n] = 0.0;
+                        } else {
+                            ul[n] = ur[n];
+                        }
+                    }
+                } else if (bc == P_NOSLIPWALL) {
+                    for (int n = 0; n < dim; ++n) ul[n] = ur[n] = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    ur[d] = dmin_(ur[d], 0.0);
+                    if (dim == 2 && d == 0) {
+                        // QUIRK: the 2-D x sweep copies left over right here (:380-385)
+                        for (int n = 0; n < dim; ++n) ur[n] = ul[n];
+                    } else {
+                        for (int n = 0; n < dim; ++n) ul[n] = ur[n];
+                    }
+                }
+            } else if (I == g.dhi[d] + 1) {
+                const int bc = e.pbc_hi[d];
+                if (bc == P_INFLOW) {
+                    for (int n = 0; n < dim; ++n) ul[n] = ur[n] = at(utilde, f, n);
+                } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
+                    for (int n = 0; n < dim; ++n) {
+                        if (n == d) {
+                            ul[n] = 0.0;
+                            ur[n] = 0.0;
+                        } else {
+                            ur[n] = ul[n];
+                        }
+                    }
+                } else if (bc == P_NOSLIPWALL) {
+                    for (int n = 0; n < dim; ++n) ul[n] = ur[n] = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    ul[d] = dmax_(ul[d], 0.0);
+                    for (int n = 0; n < dim; ++n) ur[n] = ul[n];
+                }
+            }
+            const double t = at(utr[d], f);
+            for (int n = 0; n < dim; ++n) {
+                W.ul(d, n, f) = ul[n];
+                W.ur(d, n, f) = ur[n];
+                if (n != d) W.imh(d, n, f) = upwind_trans(t, ul[n], ur[n], e.eps);
+            }
+        }
+    });
+
+    // ---- VelPredTransverse (3-D): component c on d faces, corrected by the e derivative ----
+    if (dim == 3) {
+        for_box(obx, st, [=] __device__(int i, int j, int k) {
+            const DFab utr[3] = {ut0, ut1, ut2};
+            const I3 f = mk(i, j, k);
+            const double dt6 = e.dt / 6.0;
+            for (int c = 0; c < 3; ++c) {
+                for (int d = 0; d < 3; ++d) {
+                    if (d == c) continue;
+                    const int t = 3 - c - d;  // the transverse direction
+                    // amrex::grow(tilebox, c, 1) with growHi(d, 1)
+                    Box3 b = vb;
+                    b.lo[c] -= 1;
+                    b.hi[c] += 1;
+                    b.hi[d] += 1;
+                    if (!inside(b, f)) continue;
+                    const I3 cl = sh(f, d, -1);
+                    const double ht = g.dx[t];
+                    double l = W.ul(d, c, f) - (dt6 / ht) * (at(utr[t], sh(cl, t, 1)) + at(utr[t], cl)) *
+                                                  (W.imh(t, c, sh(cl, t, 1)) - W.imh(t, c, cl));
+                    double r = W.ur(d, c, f) - (dt6 / ht) * (at(utr[t], sh(f, t, 1)) + at(utr[t], f)) *
+                                                  (W.imh(t, c, sh(f, t, 1)) - W.imh(t, c, f));
+                    const int I = f.v[d];
+                    if (I == g.dlo[d]) {
+                        const int bc = e.pbc_lo[d];
+                        if (bc == P_INFLOW) {
+                            l = r = at(utilde, cl, c);
+                        } else if (bc == P_SLIPWALL || bc == P_SYMMETRY || bc == P_OUTFLOW) {
+                            l = r;
+                        } else if (bc == P_NOSLIPWALL) {
+                            l = r = 0.0;
+                        }
+                    } else if (I == g.dhi[d] + 1) {
+                        const int bc = e.pbc_hi[d];
+                        if (bc == P_INFLOW) {
+                            l = r = at(utilde, f, c);
+                        } else if (bc == P_SLIPWALL || bc == P_SYMMETRY || bc == P_OUTFLOW) {
+                            r = l;
+                        } else if (bc == P_NOSLIPWALL) {
+                            l = r = 0.0;
+                        }
+                    }
+                    W.tr(c, d, f) = upwind_trans(at(utr[d], f), l, r, e.eps);
+                }
+            }
+        });
+    }
+
+    // ---- VelPredVelocities: the normal component on the faces of the valid box ---------------
+    Box3 fb = vb;
+    for (int d = 0; d < dim; ++d) fb.hi[d] += 1;
+    for_box(fb, st, [=] __device__(int i, int j, int k) {
+        const DFab utr[3] = {ut0, ut1, ut2};
+        const DFab um[3] = {um0, um1, um2};
+        const DFab wmac[3] = {wm0, wm1, wm2};
+        const I3 f = mk(i, j, k);
+        const double dt2 = 0.5 * e.dt, dt4 = 0.25 * e.dt;
+        for (int d = 0; d < dim; ++d) {
+            // mfi.nodaltilebox(d)
+            bool in = true;
+            for (int q = 0; q < dim; ++q)
+                if (q != d && f.v[q] > vb.hi[q]) in = false;
+            if (!in) continue;
+            const I3 cl = sh(f, d, -1);
+            double fl, fr;
+            if (e.trace == 0) {
+                fl = at(force, cl, d);
+                fr = at(force, f, d);
+            } else {
+                fl = recon(g, e, force, ufull, d, d, cl).ip;
+                fr = recon(g, e, force, ufull, d, d, f).im;
+            }
+            double l = W.ul(d, d, f), r = W.ur(d, d, f);
+            for (int t = 0; t < dim; ++t) {  // transverse directions in ascending order
+                if (t == d) continue;
+                const double ht = g.dx[t];
+                double dl, dr;
+                if (dim == 3) {
+                    dl = W.tr(d, t, sh(cl, t, 1)) - W.tr(d, t, cl);
+                    dr = W.tr(d, t, sh(f, t, 1)) - W.tr(d, t, f);
+                } else {
+                    dl = W.imh(t, d, sh(cl, t, 1)) - W.imh(t, d, cl);
+                    dr = W.imh(t, d, sh(f, t, 1)) - W.imh(t, d, f);
+                }
+                l = l - (dt4 / ht) * (at(utr[t], sh(cl, t, 1)) + at(utr[t], cl)) * dl;
+                r = r - (dt4 / ht) * (at(utr[t], sh(f, t, 1)) + at(utr[t], f)) * dr;
+            }
+            l = l + dt2 * fl;
+            r = r + dt2 * fr;
+            double v = riemann_full(l, r, w0_term(g, e, wmac, w0c, d, f), e.eps);
+            const int I = f.v[d];
+            if (I == g.dlo[d]) {
+                const int bc = e.pbc_lo[d];
+                if (bc == P_INFLOW) {
+                    v = at(utilde, cl, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    v = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    v = dmin_(r, 0.0);
+                }
+            } else if (I == g.dhi[d] + 1) {
+                const int bc = e.pbc_hi[d];
+                if (bc == P_INFLOW) {
+                    v = at(utilde, f, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    v = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    v = dmax_(l, 0.0);
+                }
+            }
+            at(um[d], f) = v;
+        }
+    });
+}

@@ -93,7 +93,8 @@ EOF2
 fi
 
 # 2c. the companion overlay on top: ConvertRhoXToX / ConvertRhoHToH /
-#     PutInPertForm, ModifyScalForce, Put1dArrayOnCart / Addw0 / MakeW0mac / MakeS0mac, UpdateVel on
+#     PutInPertForm, ModifyScalForce, Put1dArrayOnCart / Addw0 / MakeW0mac / MakeS0mac, UpdateVel,
+#     MakeUtrans and VelPred on
 #     libmxadv.so.  They share translation units with members that stay the reference's, so those
 #     reference files are compiled with the overlaid members renamed.
 if [ "$DIM" = 3 ]; then BASE=fx; else BASE=mx; fi
@@ -101,7 +102,7 @@ rm -rf "$WORK/${TAGP}cx$DIM"
 cp -r "$WORK/${TAGP}${BASE}$DIM" "$WORK/${TAGP}cx$DIM"
 cd "$WORK/${TAGP}cx$DIM"
 rm -f Maestro${DIM}d.gnu.OMP.ex
-for f in MaestroConvert MaestroForce MaestroFill3dData MaestroAdvection; do
+for f in MaestroConvert MaestroForce MaestroFill3dData MaestroAdvection MaestroMakeUtrans MaestroVelPred; do
     find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
 done
 python3 - "$REPO" <<'EOF3'
@@ -117,6 +118,8 @@ $(objEXETempDir)/MaestroAdvection.o: CPPFLAGS += -DUpdateVel=UpdateVel_reference
 $(objEXETempDir)/MaestroConvert.o: CPPFLAGS += -DConvertRhoXToX=ConvertRhoXToX_reference -DConvertRhoHToH=ConvertRhoHToH_reference -DPutInPertForm=PutInPertForm_reference
 $(objEXETempDir)/MaestroForce.o: CPPFLAGS += -DModifyScalForce=ModifyScalForce_reference
 $(objEXETempDir)/MaestroFill3dData.o: CPPFLAGS += -DPut1dArrayOnCart=Put1dArrayOnCart_reference -DAddw0=Addw0_reference -DMakeW0mac=MakeW0mac_reference -DMakeS0mac=MakeS0mac_reference
+$(objEXETempDir)/MaestroMakeUtrans.o: CPPFLAGS += -DMakeUtrans=MakeUtrans_reference
+$(objEXETempDir)/MaestroVelPred.o: CPPFLAGS += -DVelPred=VelPred_reference
 """
 assert key in mk
 open("GNUmakefile", "w").write(mk.replace(key, add + key) + tail)

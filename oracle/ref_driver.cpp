@@ -669,6 +669,73 @@ int DRV(update_vel)(const MxGeom* g, const MxFab* uold, const MxFab* unew, const
     m.UpdateVel(um, ue, fo, sp, wm);
     return 0;
 }
+
+// Maestro::MakeUtrans (Source/MaestroMakeUtrans.cpp:6) and Maestro::VelPred
+// (Source/MaestroVelPred.cpp:5)
+namespace {
+void set_vel(Maestro& m, const MxVelPredParams* p) {
+    m.dt = p->dt;
+    m.rel_eps = p->rel_eps;
+    maestro::ppm_type = p->ppm_type;
+    maestro::slope_order = p->slope_order;
+    maestro::ppm_trace_forces = p->ppm_trace_forces;
+    maestro::spherical = p->spherical != 0;
+    m.bcs_u.resize(DIM);
+    for (int n = 0; n < DIM; ++n) {
+        for (int d = 0; d < DIM; ++d) {
+            m.bcs_u[n].setLo(d, p->bc[6 * n + d]);
+            m.bcs_u[n].setHi(d, p->bc[6 * n + 3 + d]);
+        }
+    }
+    for (int d = 0; d < DIM; ++d) {
+        m.phys_bc.setLo(d, p->phys_bc_lo[d]);
+        m.phys_bc.setHi(d, p->phys_bc_hi[d]);
+    }
+}
+}  // namespace
+
+int DRV(make_utrans)(const MxGeom* g, const MxFab* utilde, const MxFab* ufull, const MxFab* utrans,
+                     const MxFab* w0_cart, const MxFab* w0mac, const MxVelPredParams* p) {
+    Maestro m;
+    setup(m, g);
+    set_vel(m, p);
+    Vector<MultiFab> ut(1), uf(1);
+    alias(ut[0], g, utilde, -1);
+    alias(uf[0], g, ufull, -1);
+    Vector<std::array<MultiFab, DIM>> tr, wm;
+    alias_faces(tr, g, utrans);
+    alias_faces(wm, g, p->spherical ? w0mac : nullptr);
+    m.w0_cart.resize(1);
+    if (w0_cart)
+        alias(m.w0_cart[0], g, w0_cart, -1);
+    else
+        m.w0_cart[0].define(m.grids[0], m.dmap[0], DIM, 1);
+    m.MakeUtrans(ut, uf, tr, wm);
+    return 0;
+}
+
+int DRV(vel_pred)(const MxGeom* g, const MxFab* utilde, const MxFab* ufull, const MxFab* utrans,
+                  const MxFab* umac, const MxFab* w0mac, const MxFab* w0_cart, const MxFab* force,
+                  const MxVelPredParams* p) {
+    Maestro m;
+    setup(m, g);
+    set_vel(m, p);
+    Vector<MultiFab> ut(1), uf(1), fo(1);
+    alias(ut[0], g, utilde, -1);
+    alias(uf[0], g, ufull, -1);
+    alias(fo[0], g, force, -1);
+    Vector<std::array<MultiFab, DIM>> tr, um, wm;
+    alias_faces(tr, g, utrans);
+    alias_faces(um, g, umac);
+    alias_faces(wm, g, p->spherical ? w0mac : nullptr);
+    m.w0_cart.resize(1);
+    if (w0_cart)
+        alias(m.w0_cart[0], g, w0_cart, -1);
+    else
+        m.w0_cart[0].define(m.grids[0], m.dmap[0], DIM, 1);
+    m.VelPred(ut, uf, tr, um, wm, fo);
+    return 0;
+}
 #endif  // !DRV_OVERLAY
 
 #ifndef DRV_OVERLAY
