@@ -94,7 +94,7 @@ def main():
            "peak_GBps": peak}
     from oracle import backends
     ref = backends.reference(3)
-    if ref is not None:
+    if ref is not None and a.cpu_size > 0:
         import numpy as np
         ref.lib.ref_set_num_threads(os.cpu_count() or 1)
         C = problem(a.cpu_size, a.ppm, np)
