@@ -69,6 +69,10 @@ struct FusedArgs {
     int nzc;           // number of z chunks
     int ntx, nty;  // number of tiles
     int bcdir[3];  // some swept component has a non-interior BC in this direction
+    // plane strides in BYTES of umac[0..2], force, sedge[0..2], sflux[0..2], eta: the streaming
+    // kernel advances its running pointers by these, which the compiler can then use straight
+    // from the constant bank (no LDC + shift per pointer and plane)
+    long bs[11];
     alignas(64) CUtensorMap tmap_state;  // (x, y, z, comp) view of `state` for the TMA ring fill
 };
 
@@ -175,6 +179,11 @@ int dispatch(FusedArgs& A, int ppm_type, cudaStream_t stream) {
     const int nx = A.g.vhi[0] - A.g.vlo[0] + 1, ny = A.g.vhi[1] - A.g.vlo[1] + 1;
     A.ntx = (nx + 29) / 30;
     A.nty = (ny + (S4_GY - 2) - 1) / (S4_GY - 2);
+    {
+        const DFab* f[11] = {&A.umac[0], &A.umac[1], &A.umac[2], &A.force, &A.sedge[0], &A.sedge[1],
+                             &A.sedge[2], &A.sflux[0], &A.sflux[1], &A.sflux[2], &A.eta};
+        for (int q = 0; q < 11; ++q) A.bs[q] = f[q]->sz * (long)sizeof(double);
+    }
     if (A.zc > ST_MAXZC) A.zc = ST_MAXZC;
     set_zchunks(A, true);
     if (ppm_type == 0) return launch_stream4_mode<0>(A, stream);

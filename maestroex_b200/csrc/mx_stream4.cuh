@@ -79,6 +79,9 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     unsigned long long* const mbar =
         reinterpret_cast<unsigned long long*>(tab + 5 * (ST_MAXZC + 2) + 2);  // one per ring slot (TMA)
 
+    // p advanced by one plane (byte stride taken from the kernel parameters)
+#define S4_ADV(p_, bytes_) \
+    p_ = reinterpret_cast<decltype(p_)>(reinterpret_cast<uintptr_t>(p_) + (uintptr_t)(bytes_))
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
     double* const hs = hist + tid;
@@ -122,12 +125,9 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
     const bool neary = BC && ((j <= g.dlo[1] + 4) || (j >= g.dhi[1] - 4));  // j is per warp
 
     const DFab& st = A.state;
-    const long st_sz = st.sz, f_sz = A.force.sz;
-    const long u_sz = A.umac[0].sz, v_sz = A.umac[1].sz, w_sz = A.umac[2].sz;
+    const long st_sz = st.sz;
+    const long w_sz = A.umac[2].sz;
     const long v_sy = A.umac[1].sy;
-    const long ex_sz = A.sedge[0].sz, ey_sz = A.sedge[1].sz, ez_sz = A.sedge[2].sz;
-    const long fx_sz = A.sflux[0].sz, fy_sz = A.sflux[1].sz, fz_sz = A.sflux[2].sz;
-    const long eta_sz = A.eta.sz;
     const KFlux& F_ = A.f;
     constexpr bool sph = SPH;  // spherical flux forms (density pass only; compile-time so that
                                // the planar instantiation carries no dead loads / registers)
@@ -367,10 +367,10 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
             if (a < k1) {  // block uniform
                 stage_plane(it + 2 * LA + 1);  // plane a+LA+1
 #endif
-                pU += u_sz;
-                pV += v_sz;
-                pW += w_sz;
-                pF += f_sz;
+                S4_ADV(pU, A.bs[0]);
+                S4_ADV(pV, A.bs[1]);
+                S4_ADV(pW, A.bs[2]);
+                S4_ADV(pF, A.bs[3]);
                 um_n = pU[0];
                 if (lane31) up31_n = pU[1];
                 vm_n = pV[0];
@@ -712,14 +712,14 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
                 }
             }
             // advance the output pointers to the next plane
-            pEx += ex_sz;
-            pEy += ey_sz;
-            pEz += ez_sz;
+            S4_ADV(pEx, A.bs[4]);
+            S4_ADV(pEy, A.bs[5]);
+            S4_ADV(pEz, A.bs[6]);
             if (MODE != 0) {
-                pFx += fx_sz;
-                pFy += fy_sz;
-                pFz += fz_sz;
-                if (MODE == 1) pEta += eta_sz;
+                S4_ADV(pFx, A.bs[7]);
+                S4_ADV(pFy, A.bs[8]);
+                S4_ADV(pFz, A.bs[9]);
+                if (MODE == 1) S4_ADV(pEta, A.bs[10]);
             }
 
             // ---- z history for the next plane -----------------------------------------------
@@ -741,6 +741,7 @@ __device__ __forceinline__ void stream4_body(const FusedArgs& A, double* smem) {
         if (!TMA) cp_async_wait<0>();
     }
 #undef HS
+#undef S4_ADV
 }
 
 template <int PPM, int MODE, bool SPH, bool TMA>

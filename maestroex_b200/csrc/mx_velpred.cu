@@ -79,6 +79,14 @@ MXD bool inside(const Box3& b, const I3& c) {
            c.v[2] >= b.lo[2] && c.v[2] <= b.hi[2];
 }
 
+// three fabs captured by value in a kernel lambda: with the direction loops unrolled every
+// index is a compile-time constant and the fab is read from the kernel parameters (per-thread
+// arrays of fabs cost ~200 B of local-memory stores per thread: that was most of the first
+// version's run time, profiles/r2_velpred.json)
+struct F3 {
+    DFab f[3];
+};
+
 // workspace arrays over the grown box
 struct WS {
     double* p;
@@ -145,9 +153,10 @@ MXD RC recon(const KGeom& g, const KVel& e, const DFab& s, const DFab& uf, int n
 
 // the w0 term of the Riemann problems: w0mac on spherical grids, w0_cart's last component in
 // the last direction of planar ones, nothing otherwise (MaestroVelPred.cpp:1651-1667, :1860-1884)
-MXD double w0_term(const KGeom& g, const KVel& e, const DFab* w0mac, const DFab& w0c, int d, const I3& f) {
-    if (e.spherical) return at(w0mac[d], f);
-    if (d == g.dim - 1) return at(w0c, f, g.dim - 1);
+template <int DIM>
+MXD double w0_term(const KVel& e, const F3& w0mac, const DFab& w0c, int d, const I3& f) {
+    if (e.spherical) return at(w0mac.f[d], f);
+    if (d == DIM - 1) return at(w0c, f, DIM - 1);
     return 0.0;
 }
 
@@ -172,76 +181,92 @@ size_t vel_pred_workspace(const KGeom& g) {
 }
 
 // ---- Maestro::MakeUtrans -------------------------------------------------------------------
+template <int DIM, int D>
+static void utrans_dir(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
+                       const DFab& out, const DFab& w0c, const DFab& wmac_d, cudaStream_t st) {
+    Box3 fb;
+    for (int q = 0; q < 3; ++q) {
+        fb.lo[q] = g.vlo[q];
+        fb.hi[q] = g.vhi[q] + (q == D ? 1 : 0);
+    }
+    for_box(fb, st, [=] __device__(int i, int j, int k) {
+        constexpr int d = D;
+        const I3 f = mk(i, j, k), cl = sh(f, d, -1);
+        const double dt2 = 0.5 * e.dt;
+        double l, r;
+        const RC L = recon(g, e, utilde, ufull, d, d, cl), R = recon(g, e, utilde, ufull, d, d, f);
+        if (e.ppm_type == 0) {
+            // MaestroMakeUtrans.cpp:94-103
+            l = at(utilde, cl, d) + (0.5 - (dt2 / g.dx[d]) * dmax_(0.0, at(ufull, cl, d))) * L.ip;
+            r = at(utilde, f, d) - (0.5 + (dt2 / g.dx[d]) * dmin_(0.0, at(ufull, f, d))) * R.ip;
+        } else {
+            l = L.ip;
+            r = R.im;
+        }
+        const int I = f.v[d];
+        if (I == g.dlo[d]) {
+            const int bc = e.pbc_lo[d];
+            if (bc == P_INFLOW) {
+                l = r = at(utilde, cl, d);
+            } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                // QUIRK: the 2-D y sweep zeroes only the right state (:220-221)
+                if (!(DIM == 2 && d == 1)) l = 0.0;
+                r = 0.0;
+            } else if (bc == P_OUTFLOW) {
+                l = dmin_(r, 0.0);
+                r = l;
+            }
+        } else if (I == g.dhi[d] + 1) {
+            const int bc = e.pbc_hi[d];
+            if (bc == P_INFLOW) {
+                // QUIRK: 3-D reads one cell further out (:350-351, :466-467, :581-582)
+                const I3 src = DIM == 3 ? sh(f, d, 1) : f;
+                l = r = at(utilde, src, d);
+            } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                l = 0.0;
+                r = 0.0;
+            } else if (bc == P_OUTFLOW) {
+                l = dmax_(l, 0.0);
+                r = l;
+            }
+        }
+        double w = 0.0;  // w0_term
+        if (e.spherical)
+            w = at(wmac_d, f);
+        else if (d == DIM - 1)
+            w = at(w0c, f, DIM - 1);
+        at(out, f) = riemann_full(l, r, w, e.eps);
+    });
+}
+
 void vel_make_utrans(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
                      const DFab* utrans, const DFab& w0c, const DFab* w0mac_in, cudaStream_t st) {
     DFab wm[3];
     for (int d = 0; d < 3; ++d) wm[d] = (e.spherical && w0mac_in) ? w0mac_in[d] : w0c;
-    const DFab wm0 = wm[0], wm1 = wm[1], wm2 = wm[2];
-    for (int d = 0; d < g.dim; ++d) {
-        Box3 fb;
-        for (int q = 0; q < 3; ++q) {
-            fb.lo[q] = g.vlo[q];
-            fb.hi[q] = g.vhi[q] + (q == d ? 1 : 0);
-        }
-        const DFab out = utrans[d];
-        for_box(fb, st, [=] __device__(int i, int j, int k) {
-            const DFab wmac[3] = {wm0, wm1, wm2};
-            const I3 f = mk(i, j, k), cl = sh(f, d, -1);
-            const double dt2 = 0.5 * e.dt;
-            double l, r;
-            const RC L = recon(g, e, utilde, ufull, d, d, cl), R = recon(g, e, utilde, ufull, d, d, f);
-            if (e.ppm_type == 0) {
-                // MaestroMakeUtrans.cpp:94-103
-                l = at(utilde, cl, d) + (0.5 - (dt2 / g.dx[d]) * dmax_(0.0, at(ufull, cl, d))) * L.ip;
-                r = at(utilde, f, d) - (0.5 + (dt2 / g.dx[d]) * dmin_(0.0, at(ufull, f, d))) * R.ip;
-            } else {
-                l = L.ip;
-                r = R.im;
-            }
-            const int I = f.v[d];
-            if (I == g.dlo[d]) {
-                const int bc = e.pbc_lo[d];
-                if (bc == P_INFLOW) {
-                    l = r = at(utilde, cl, d);
-                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
-                    // QUIRK: the 2-D y sweep zeroes only the right state (:220-221)
-                    if (!(g.dim == 2 && d == 1)) l = 0.0;
-                    r = 0.0;
-                } else if (bc == P_OUTFLOW) {
-                    l = dmin_(r, 0.0);
-                    r = l;
-                }
-            } else if (I == g.dhi[d] + 1) {
-                const int bc = e.pbc_hi[d];
-                if (bc == P_INFLOW) {
-                    // QUIRK: 3-D reads one cell further out (:350-351, :466-467, :581-582)
-                    const I3 src = g.dim == 3 ? sh(f, d, 1) : f;
-                    l = r = at(utilde, src, d);
-                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
-                    l = 0.0;
-                    r = 0.0;
-                } else if (bc == P_OUTFLOW) {
-                    l = dmax_(l, 0.0);
-                    r = l;
-                }
-            }
-            at(out, f) = riemann_full(l, r, w0_term(g, e, wmac, w0c, d, f), e.eps);
-        });
+    if (g.dim == 2) {
+        utrans_dir<2, 0>(g, e, utilde, ufull, utrans[0], w0c, wm[0], st);
+        utrans_dir<2, 1>(g, e, utilde, ufull, utrans[1], w0c, wm[1], st);
+    } else {
+        utrans_dir<3, 0>(g, e, utilde, ufull, utrans[0], w0c, wm[0], st);
+        utrans_dir<3, 1>(g, e, utilde, ufull, utrans[1], w0c, wm[1], st);
+        utrans_dir<3, 2>(g, e, utilde, ufull, utrans[2], w0c, wm[2], st);
     }
 }
 
 // ---- Maestro::VelPred ------------------------------------------------------------------------
-void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
-              const DFab* utrans_in, const DFab* umac_out, const DFab* w0mac_in, const DFab& w0c,
-              const DFab& force, double* wsp, cudaStream_t st) {
+template <int DIM>
+static void vel_pred_dim(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
+                         const DFab* utrans_in, const DFab* umac_out, const DFab* w0mac_in,
+                         const DFab& w0c, const DFab& force, double* wsp, cudaStream_t st) {
     const WS W = make_ws(g, wsp);
     const Box3 obx = W.b;
-    const int dim = g.dim;
-    const DFab ut0 = utrans_in[0], ut1 = utrans_in[1], ut2 = dim == 3 ? utrans_in[2] : utrans_in[1];
-    const DFab um0 = umac_out[0], um1 = umac_out[1], um2 = dim == 3 ? umac_out[2] : umac_out[1];
-    DFab wm[3];
-    for (int d = 0; d < 3; ++d) wm[d] = (e.spherical && w0mac_in) ? w0mac_in[d] : w0c;
-    const DFab wm0 = wm[0], wm1 = wm[1], wm2 = wm[2];
+    constexpr int dim = DIM;
+    F3 utr, um, wmac;
+    for (int d = 0; d < 3; ++d) {
+        utr.f[d] = utrans_in[d < DIM ? d : DIM - 1];
+        um.f[d] = umac_out[d < DIM ? d : DIM - 1];
+        wmac.f[d] = (e.spherical && w0mac_in) ? w0mac_in[d] : w0c;
+    }
     Box3 vb;
     for (int q = 0; q < 3; ++q) {
         vb.lo[q] = g.vlo[q];
@@ -251,9 +276,9 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
     // ---- VelPredInterface: ul / ur of every component on the faces of mxbx / mybx / mzbx
     // (obx with the low side of the normal direction pulled in), BCs, transverse uimh --------
     for_box(obx, st, [=] __device__(int i, int j, int k) {
-        const DFab utr[3] = {ut0, ut1, ut2};
         const I3 f = mk(i, j, k);
         const double dt2 = 0.5 * e.dt;
+#pragma unroll
         for (int d = 0; d < dim; ++d) {
             if (f.v[d] < obx.lo[d] + 1) continue;
             const I3 cl = sh(f, d, -1);
@@ -264,11 +289,13 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                 // 3-D: :785-796; 2-D association differs: :336-345
                 const double fl = dim == 3 ? 0.5 - dt2 * uL / h : 0.5 - (dt2 / h) * uL;
                 const double fr = dim == 3 ? 0.5 + dt2 * uR / h : 0.5 + (dt2 / h) * uR;
+#pragma unroll
                 for (int n = 0; n < dim; ++n) {
                     ul[n] = at(utilde, cl, n) + fl * recon(g, e, utilde, ufull, n, d, cl).ip;
                     ur[n] = at(utilde, f, n) - fr * recon(g, e, utilde, ufull, n, d, f).ip;
                 }
             } else {
+#pragma unroll
                 for (int n = 0; n < dim; ++n) {
                     ul[n] = recon(g, e, utilde, ufull, n, d, cl).ip;
                     ur[n] = recon(g, e, utilde, ufull, n, d, f).im;
@@ -278,9 +305,11 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
             if (I == g.dlo[d]) {
                 const int bc = e.pbc_lo[d];
                 if (bc == P_INFLOW) {
+#pragma unroll
                     for (int n = 0; n < dim; ++n) ul[n] = ur[n] = at(utilde, cl, n);
                 } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
-                    for (int n = 0; n < dim; ++n) {
+    #pragma unroll
+                for (int n = 0; n < dim; ++n) {
                         if (n == d) {
                             ul[n] = 0.0;
                             ur[n] = 0.0;
@@ -289,22 +318,27 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                         }
                     }
                 } else if (bc == P_NOSLIPWALL) {
+#pragma unroll
                     for (int n = 0; n < dim; ++n) ul[n] = ur[n] = 0.0;
                 } else if (bc == P_OUTFLOW) {
                     ur[d] = dmin_(ur[d], 0.0);
                     if (dim == 2 && d == 0) {
                         // QUIRK: the 2-D x sweep copies left over right here (:380-385)
-                        for (int n = 0; n < dim; ++n) ur[n] = ul[n];
+    #pragma unroll
+                    for (int n = 0; n < dim; ++n) ur[n] = ul[n];
                     } else {
-                        for (int n = 0; n < dim; ++n) ul[n] = ur[n];
+    #pragma unroll
+                    for (int n = 0; n < dim; ++n) ul[n] = ur[n];
                     }
                 }
             } else if (I == g.dhi[d] + 1) {
                 const int bc = e.pbc_hi[d];
                 if (bc == P_INFLOW) {
+#pragma unroll
                     for (int n = 0; n < dim; ++n) ul[n] = ur[n] = at(utilde, f, n);
                 } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
-                    for (int n = 0; n < dim; ++n) {
+    #pragma unroll
+                for (int n = 0; n < dim; ++n) {
                         if (n == d) {
                             ul[n] = 0.0;
                             ur[n] = 0.0;
@@ -313,13 +347,16 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                         }
                     }
                 } else if (bc == P_NOSLIPWALL) {
+#pragma unroll
                     for (int n = 0; n < dim; ++n) ul[n] = ur[n] = 0.0;
                 } else if (bc == P_OUTFLOW) {
                     ul[d] = dmax_(ul[d], 0.0);
+#pragma unroll
                     for (int n = 0; n < dim; ++n) ur[n] = ul[n];
                 }
             }
-            const double t = at(utr[d], f);
+            const double t = at(utr.f[d], f);
+#pragma unroll
             for (int n = 0; n < dim; ++n) {
                 W.ul(d, n, f) = ul[n];
                 W.ur(d, n, f) = ur[n];
@@ -329,12 +366,13 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
     });
 
     // ---- VelPredTransverse (3-D): component c on d faces, corrected by the e derivative ----
-    if (dim == 3) {
+    if constexpr (DIM == 3) {
         for_box(obx, st, [=] __device__(int i, int j, int k) {
-            const DFab utr[3] = {ut0, ut1, ut2};
-            const I3 f = mk(i, j, k);
+                const I3 f = mk(i, j, k);
             const double dt6 = e.dt / 6.0;
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
+#pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     if (d == c) continue;
                     const int t = 3 - c - d;  // the transverse direction
@@ -346,9 +384,9 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                     if (!inside(b, f)) continue;
                     const I3 cl = sh(f, d, -1);
                     const double ht = g.dx[t];
-                    double l = W.ul(d, c, f) - (dt6 / ht) * (at(utr[t], sh(cl, t, 1)) + at(utr[t], cl)) *
+                    double l = W.ul(d, c, f) - (dt6 / ht) * (at(utr.f[t], sh(cl, t, 1)) + at(utr.f[t], cl)) *
                                                   (W.imh(t, c, sh(cl, t, 1)) - W.imh(t, c, cl));
-                    double r = W.ur(d, c, f) - (dt6 / ht) * (at(utr[t], sh(f, t, 1)) + at(utr[t], f)) *
+                    double r = W.ur(d, c, f) - (dt6 / ht) * (at(utr.f[t], sh(f, t, 1)) + at(utr.f[t], f)) *
                                                   (W.imh(t, c, sh(f, t, 1)) - W.imh(t, c, f));
                     const int I = f.v[d];
                     if (I == g.dlo[d]) {
@@ -370,7 +408,7 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                             l = r = 0.0;
                         }
                     }
-                    W.tr(c, d, f) = upwind_trans(at(utr[d], f), l, r, e.eps);
+                    W.tr(c, d, f) = upwind_trans(at(utr.f[d], f), l, r, e.eps);
                 }
             }
         });
@@ -380,14 +418,13 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
     Box3 fb = vb;
     for (int d = 0; d < dim; ++d) fb.hi[d] += 1;
     for_box(fb, st, [=] __device__(int i, int j, int k) {
-        const DFab utr[3] = {ut0, ut1, ut2};
-        const DFab um[3] = {um0, um1, um2};
-        const DFab wmac[3] = {wm0, wm1, wm2};
         const I3 f = mk(i, j, k);
         const double dt2 = 0.5 * e.dt, dt4 = 0.25 * e.dt;
+#pragma unroll
         for (int d = 0; d < dim; ++d) {
             // mfi.nodaltilebox(d)
             bool in = true;
+#pragma unroll
             for (int q = 0; q < dim; ++q)
                 if (q != d && f.v[q] > vb.hi[q]) in = false;
             if (!in) continue;
@@ -401,6 +438,7 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                 fr = recon(g, e, force, ufull, d, d, f).im;
             }
             double l = W.ul(d, d, f), r = W.ur(d, d, f);
+#pragma unroll
             for (int t = 0; t < dim; ++t) {  // transverse directions in ascending order
                 if (t == d) continue;
                 const double ht = g.dx[t];
@@ -412,12 +450,12 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                     dl = W.imh(t, d, sh(cl, t, 1)) - W.imh(t, d, cl);
                     dr = W.imh(t, d, sh(f, t, 1)) - W.imh(t, d, f);
                 }
-                l = l - (dt4 / ht) * (at(utr[t], sh(cl, t, 1)) + at(utr[t], cl)) * dl;
-                r = r - (dt4 / ht) * (at(utr[t], sh(f, t, 1)) + at(utr[t], f)) * dr;
+                l = l - (dt4 / ht) * (at(utr.f[t], sh(cl, t, 1)) + at(utr.f[t], cl)) * dl;
+                r = r - (dt4 / ht) * (at(utr.f[t], sh(f, t, 1)) + at(utr.f[t], f)) * dr;
             }
             l = l + dt2 * fl;
             r = r + dt2 * fr;
-            double v = riemann_full(l, r, w0_term(g, e, wmac, w0c, d, f), e.eps);
+            double v = riemann_full(l, r, w0_term<DIM>(e, wmac, w0c, d, f), e.eps);
             const int I = f.v[d];
             if (I == g.dlo[d]) {
                 const int bc = e.pbc_lo[d];
@@ -438,7 +476,16 @@ void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufu
                     v = dmax_(l, 0.0);
                 }
             }
-            at(um[d], f) = v;
+            at(um.f[d], f) = v;
         }
     });
+}
+
+void vel_pred(const KGeom& g, const KVel& e, const DFab& utilde, const DFab& ufull,
+              const DFab* utrans, const DFab* umac, const DFab* w0mac, const DFab& w0c,
+              const DFab& force, double* ws, cudaStream_t st) {
+    if (g.dim == 2)
+        vel_pred_dim<2>(g, e, utilde, ufull, utrans, umac, w0mac, w0c, force, ws, st);
+    else
+        vel_pred_dim<3>(g, e, utilde, ufull, utrans, umac, w0mac, w0c, force, ws, st);
 }

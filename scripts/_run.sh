@@ -1,5 +1,10 @@
-O=gpurun_out/vp2; mkdir -p $O
-timeout -k 10 600 python -m pytest tests/test_velpred.py -q -m gpu 2>&1 | tail -4 | cut -c1-300 | tee $O/pytest_velpred.log
-MXADV_FCOMPARE_OUT=$O/fcompare timeout -k 10 1500 python -m pytest tests/test_gpu_fcompare.py tests/test_ci_extrema.py -q -m gpu -k "cx" 2>&1 | tail -15 | cut -c1-400 | tee $O/pytest_cx.log
-timeout -k 10 300 python tools/bench_velpred.py --size 256 --ppm 1 > $O/velpred_256_ppm1.json 2> $O/velpred.err; cat $O/velpred_256_ppm1.json; tail -3 $O/velpred.err
-timeout -k 10 300 python tools/bench_velpred.py --size 256 --ppm 0 --cpu-size 0 > $O/velpred_256_ppm0.json 2>> $O/velpred.err; cat $O/velpred_256_ppm0.json
+O=gpurun_out/e2e2; mkdir -p $O
+timeout -k 10 900 python -m pytest tests/test_gpu_advance.py tests/test_gpu_pipeline.py tests/test_velpred.py -x -q -m gpu 2>&1 | tail -3 | tee $O/pytest.log
+for t in 1 2 3 4 8; do
+timeout -k 10 600 python bench.py --size 256 --steps 5 --warmup 3 --no-cpu --e2e-threads $t > $O/bench_t$t.json 2> $O/bench_t$t.err
+python - <<PY
+import json
+d=json.loads(open('$O/bench_t$t.json').read().strip().splitlines()[-1])
+print($t, 'e2e', d['e2e']['value'], 'members', d['e2e']['members']['value'])
+PY
+done
