@@ -4,6 +4,7 @@
 # GNU-make system as a CUDA application for sm_100 (USE_CUDA=TRUE CUDA_ARCH=100
 # TINY_PROFILE=TRUE, no MPI / OpenMP), twice:
 #   Maestro3d.cuda.ref.ex  the UNMODIFIED reference: its own ParallelFor lambdas on the B200
+#   Maestro3d.cuda.cx.ex   mx + overlay_fused + overlay_companions (every layer of INTEGRATION.md)
 #   Maestro3d.cuda.mx.ex   the same build with maestroex_b200/overlay/ shadowing the hot path,
 #                          linked against libmxadv.so; fabs are AMReX device memory, so the
 #                          library runs on them in place on amrex::Gpu::gpuStream()
@@ -90,6 +91,34 @@ open("GNUmakefile", "w").write(mk.replace(key, add + key))
 EOF
 $MK > build_fx.log 2>&1
 cp Maestro3d.gnu.TPROF.CUDA.ex "$OUT/Maestro3d.cuda.fx.ex"
+# 4. the companion overlay on top (SURVEY.md section 8f ranks 2-4 incl. MakeUtrans / VelPred), as
+#    step 2c of build_e2e.sh
+rm -rf "$WORK/rb_cudacx3"
+cp -r "$WORK/rb_cudafx3" "$WORK/rb_cudacx3"
+cd "$WORK/rb_cudacx3"
+rm -f Maestro3d.gnu.TPROF.CUDA.ex
+for f in MaestroConvert MaestroForce MaestroFill3dData MaestroAdvection MaestroMakeUtrans MaestroVelPred; do
+    find tmp_build_dir \( -name "$f.o" -o -name "$f.d" \) -delete
+done
+python3 - <<'EOF'
+mk = open("GNUmakefile").read()
+key = "LIBRARIES         += -lmxadv"
+add = """Bpack   += $(MXADV_HOME)/maestroex_b200/overlay_companions/Make.package
+Blocs   += $(MXADV_HOME)/maestroex_b200/overlay_companions
+"""
+tail = """
+$(objEXETempDir)/MaestroAdvection.o: CPPFLAGS += -DUpdateVel=UpdateVel_reference
+$(objEXETempDir)/MaestroConvert.o: CPPFLAGS += -DConvertRhoXToX=ConvertRhoXToX_reference -DConvertRhoHToH=ConvertRhoHToH_reference -DPutInPertForm=PutInPertForm_reference
+$(objEXETempDir)/MaestroForce.o: CPPFLAGS += -DModifyScalForce=ModifyScalForce_reference
+$(objEXETempDir)/MaestroFill3dData.o: CPPFLAGS += -DPut1dArrayOnCart=Put1dArrayOnCart_reference -DAddw0=Addw0_reference -DMakeW0mac=MakeW0mac_reference -DMakeS0mac=MakeS0mac_reference
+$(objEXETempDir)/MaestroMakeUtrans.o: CPPFLAGS += -DMakeUtrans=MakeUtrans_reference
+$(objEXETempDir)/MaestroVelPred.o: CPPFLAGS += -DVelPred=VelPred_reference
+"""
+assert key in mk
+open("GNUmakefile", "w").write(mk.replace(key, add + key) + tail)
+EOF
+$MK > build_cx.log 2>&1 || { tail -30 build_cx.log; exit 1; }
+cp Maestro3d.gnu.TPROF.CUDA.ex "$OUT/Maestro3d.cuda.cx.ex"
 cp "$WORK/rb_cuda3/inputs_3d_C" "$WORK/rb_cuda3/model.hse.cool.coulomb" "$OUT/"
 [ -f "$OUT/helm_table.dat.gz" ] || gzip -c "$REF/external/Microphysics/EOS/helmholtz/helm_table.dat" > "$OUT/helm_table.dat.gz"
 strip "$OUT"/Maestro3d.cuda.*.ex

@@ -51,10 +51,13 @@ out, tag = sys.argv[1:3]
 names = ["Maestro::MakeEdgeScal()", "Maestro::MakeRhoXFlux()", "Maestro::MakeRhoHFlux()",
          "Maestro::UpdateScal()", "Maestro::Makew0()", "Maestro::CelltoEdge()",
          "Maestro::DensityAdvance()", "Maestro::EnthalpyAdvance()", "Maestro::VelocityAdvance()",
-         "Maestro::AdvanceTimeStep()", "Maestro::Evolve()"]
+         "Maestro::AdvancePremac()", "Maestro::MakeUtrans()", "Maestro::VelPred()",
+         "Maestro::MakeVelForce()", "Maestro::UpdateVel()", "Maestro::ModifyScalForce()",
+         "Maestro::Put1dArrayOnCart()", "Maestro::Addw0()", "Maestro::MacProj()", "Maestro::NodalProj()",
+         "Maestro::React()", "Maestro::AdvanceTimeStep()", "Maestro::Evolve()"]
 res = {}
 import os
-arms = [a for a in ("ref", "mx", "fx") if os.path.exists(f"{out}/run_{tag}_{a}.log")]
+arms = [a for a in ("ref", "mx", "fx", "cx") if os.path.exists(f"{out}/run_{tag}_{a}.log")]
 for arm in arms:
     txt = open(f"{out}/run_{tag}_{arm}.log").read()
     # second TinyProfiler table = inclusive times: name ncalls min avg max pct
