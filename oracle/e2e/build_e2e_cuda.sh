@@ -122,4 +122,5 @@ cp Maestro3d.gnu.TPROF.CUDA.ex "$OUT/Maestro3d.cuda.cx.ex"
 cp "$WORK/rb_cuda3/inputs_3d_C" "$WORK/rb_cuda3/model.hse.cool.coulomb" "$OUT/"
 [ -f "$OUT/helm_table.dat.gz" ] || gzip -c "$REF/external/Microphysics/EOS/helmholtz/helm_table.dat" > "$OUT/helm_table.dat.gz"
 strip "$OUT"/Maestro3d.cuda.*.ex
+for f in "$OUT"/Maestro3d.cuda.*.ex; do xz -T0 -3 -f "$f"; done  # 165 MB -> 36 MB each (gpurun snapshot limit)
 ls -la "$OUT"

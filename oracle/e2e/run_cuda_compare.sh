@@ -24,9 +24,12 @@ TMP=$(mktemp -d)
 gunzip -c "$E2E/helm_table.dat.gz" > "$TMP/helm_table.dat"
 for arm in $ARMS; do
     mkdir -p "$TMP/$arm"
+    # the CUDA executables travel xz-compressed (165 MB each otherwise: gpurun's snapshot limit)
+    EXE="$E2E/Maestro3d.cuda.$arm.ex"
+    if [ ! -x "$EXE" ] && [ -f "$EXE.xz" ]; then xz -dc "$EXE.xz" > "$TMP/Maestro3d.cuda.$arm.ex"; chmod +x "$TMP/Maestro3d.cuda.$arm.ex"; EXE="$TMP/Maestro3d.cuda.$arm.ex"; fi
     cp "$E2E/inputs_3d_C" "$E2E/model.hse.cool.coulomb" "$TMP/$arm/"
     ln -s "$TMP/helm_table.dat" "$TMP/$arm/helm_table.dat"
-    (cd "$TMP/$arm" && timeout 900 "$E2E/Maestro3d.cuda.$arm.ex" inputs_3d_C \
+    (cd "$TMP/$arm" && timeout 900 "$EXE" inputs_3d_C \
         maestro.max_step=$NSTEPS maestro.plot_int=$NSTEPS maestro.chk_int=-1 maestro.plot_deltat=-1 \
         tiny_profiler.device_synchronize_around_region=1 amrex.fpe_trap_invalid=0 \
         amrex.the_arena_is_managed=1 amrex.the_arena_init_size=4294967296 "$@" \
