@@ -1,2 +1,3 @@
-O=gpurun_out/cuda2; mkdir -p $O
-ARMS="ref cx" NSTEPS=10 timeout -k 10 1500 bash oracle/e2e/run_cuda_compare.sh $O big128 "amr.n_cell=128 128 1024" amr.max_grid_size=128 2>&1 | tail -40 | cut -c1-220
+O=gpurun_out/adv3; mkdir -p $O
+MXADV_TRACE=1 timeout -k 10 600 python bench.py --size 128 --steps 1 --warmup 1 --no-cpu --e2e-boxes 2 > $O/bench.json 2> $O/trace.err
+grep -n "pipeline" $O/trace.err | tail -60
