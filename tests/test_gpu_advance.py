@@ -36,7 +36,7 @@ def _prep(ppm, nspec, n, bck, seed):
     return prob
 
 
-@pytest.mark.parametrize("residency", ["device", "host"])
+@pytest.mark.parametrize("residency", ["device", "host", "host_pinned"])
 @pytest.mark.parametrize("ppm,nspec,n,bck,spt,zero_flag", [
     (1, 3, (34, 30, 33), "reacting_bubble", 1, True),
     (1, 13, (40, 24, 20), "periodic", 1, False),
@@ -72,8 +72,12 @@ def test_density_advance(mx, oracle_calls, ppm, nspec, n, bck, spt, zero_flag, r
         got_new, got_eta = to_host([got_new])[0], to_host([got_eta])[0]
     else:
         _, _, eta = prob.clone_outputs()
-        got_new, got_eta = density_advance(mx, prob, snew, epar, fpar, upar, species_force_is_zero=zero_flag,
+        hprob = prob
+        if residency == "host_pinned":
+            hprob, snew, eta = pinned_problem(prob), pinned_fab(snew), pinned_fab(eta)
+        got_new, got_eta = density_advance(mx, hprob, snew, epar, fpar, upar, species_force_is_zero=zero_flag,
                                            outputs=(None, None, eta))
+        got_new, got_eta = as_numpy(got_new), as_numpy(got_eta)
     v = _valid(prob, got_new)
     comps = [RHO] + list(range(FIRSTSPEC, FIRSTSPEC + nspec))
     for c in comps:
@@ -83,12 +87,31 @@ def test_density_advance(mx, oracle_calls, ppm, nspec, n, bck, spt, zero_flag, r
     assert (got_new.data[1:FIRSTSPEC] == -7.0).all()
 
 
+def pinned_fab(f):
+    """the same fab in page-locked host memory (what a CUDA-aware host application registers):
+    the library then returns valid zones with zero-copy stores instead of strided copies"""
+    import torch
+    return Fab(torch.from_numpy(np.ascontiguousarray(f.data)).pin_memory(), f.lo, f.hi)
+
+
+def pinned_problem(prob):
+    import copy
+    p = copy.copy(prob)
+    p.state, p.force = pinned_fab(prob.state), pinned_fab(prob.force)
+    p.umac = [pinned_fab(f) for f in prob.umac]
+    return p
+
+
+def as_numpy(f):
+    return Fab(f.data.numpy() if hasattr(f.data, "numpy") else f.data, f.lo, f.hi)
+
+
 def to_device_fab(f):
     import torch
     return Fab(torch.from_numpy(np.ascontiguousarray(f.data)).cuda(), f.lo, f.hi)
 
 
-@pytest.mark.parametrize("residency", ["device", "host"])
+@pytest.mark.parametrize("residency", ["device", "host", "host_pinned"])
 @pytest.mark.parametrize("ppm,ept,n,cut", [(1, 1, (34, 30, 26), 0.0), (1, 0, (34, 30, 26), 0.6),
                                            (2, 1, (32, 18, 40), 0.6), (0, 1, (20, 34, 33), 0.0)])
 def test_enthalpy_advance(mx, oracle_calls, ppm, ept, n, cut, residency):
@@ -127,8 +150,11 @@ def test_enthalpy_advance(mx, oracle_calls, ppm, ept, n, cut, residency):
         got_n = enthalpy_advance(mx, dprob, dnew, dfu, epar, fpar, upar, eos_mask=dmask)
         got_new, mask = to_host([dnew])[0], dmask.cpu().numpy()
     else:
-        got_n = enthalpy_advance(mx, prob, snew, fupd, epar, fpar, upar, eos_mask=mask)
-        got_new = snew
+        hprob = prob
+        if residency == "host_pinned":
+            hprob, snew, fupd = pinned_problem(prob), pinned_fab(snew), pinned_fab(fupd)
+        got_n = enthalpy_advance(mx, hprob, snew, fupd, epar, fpar, upar, eos_mask=mask)
+        got_new = as_numpy(snew)
     v = _valid(prob, got_new)
     assert got_n == want_n
     assert np.array_equal(mask, want_mask)
