@@ -14,7 +14,12 @@
 // (PPM with is_umac = false: both characteristic integrals use the cell-centred velocity,
 // MaestroPPM.cpp:233-251), so only the interface states (ul, ur, uimh) and the six
 // corner-coupled states go through device workspace.  One thread per zone of the grown box,
-// i fastest; three launches per VelPred call, one per MakeUtrans call.
+// i fastest; three launches per VelPred call (two in 2-D), one per direction for MakeUtrans.
+// Kernels are instantiated per dimension with the direction / component loops unrolled, so that
+// fab descriptors are read from the kernel parameters and the small per-thread arrays live in
+// registers.  256^3, ppm_type 1: MakeUtrans 1.25 ms, VelPred 6.8 ms (interface 4.7, transverse
+// 1.2, velocities 1.0; profiles/r2_velpred_launches.csv) = 130x the reference on 16 host threads;
+// the interface stage still forms every parabola twice (once from either face).
 //
 // Parity contract as in mx_device.cuh: reference expression trees (association included: the
 // 2-D and 3-D slope extrapolations differ, MaestroVelPred.cpp:336-345 vs :785-796), -fmad=false,
