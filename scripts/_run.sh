@@ -1,5 +1,10 @@
-O=gpurun_out/san1; mkdir -p $O
-timeout -k 10 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file $O/memcheck_velpred.txt python -m pytest tests/test_velpred.py -q -m gpu -x -k "device or golden" 2>&1 | tail -4 | cut -c1-200
-tail -5 $O/memcheck_velpred.txt
-timeout -k 10 600 compute-sanitizer --tool initcheck --error-exitcode 9 --log-file $O/initcheck_velpred.txt python -m pytest tests/test_velpred.py -q -m gpu -x -k "device and (3d-ppm1 or 2d-ppm1 or sph-ppm1)" 2>&1 | tail -3 | cut -c1-200
-tail -5 $O/initcheck_velpred.txt
+O=gpurun_out/async1; mkdir -p $O
+for i in 1 2 3; do
+MXADV_ASYNC_HOST=1 timeout -k 10 600 python bench.py --size 128 --steps 5 --warmup 3 --no-cpu --e2e-threads 2 > $O/bench_$i.json 2> $O/err.log
+python - <<PY
+import json
+d=json.loads(open('$O/bench_$i.json').read().strip().splitlines()[-1])
+print('async run $i e2e', d['e2e']['value'], 'members', d['e2e']['members']['value'])
+PY
+done
+tail -3 $O/err.log
