@@ -12,14 +12,14 @@
 // direction as MultiFabs first; here a face forms the parabola (or slope) of its two
 // neighbouring cells on the fly from the shared reconstruction of mx_device.cuh
 // (PPM with is_umac = false: both characteristic integrals use the cell-centred velocity,
-// MaestroPPM.cpp:233-251), so only the interface states (ul, ur, uimh) and the six
-// corner-coupled states go through device workspace.  One thread per zone of the grown box,
-// i fastest; three launches per VelPred call (two in 2-D), one per direction for MakeUtrans.
+// MaestroPPM.cpp:233-251); in VelPred every cell forms each parabola once and scatters Ip / Im
+// straight into the interface states of its two faces, so only the interface states (ul, ur,
+// uimh) and the six corner-coupled states go through device workspace.  One thread per zone of the grown box,
+// i fastest; four launches per VelPred call (three in 2-D), one per direction for MakeUtrans.
 // Kernels are instantiated per dimension with the direction / component loops unrolled, so that
 // fab descriptors are read from the kernel parameters and the small per-thread arrays live in
-// registers.  256^3, ppm_type 1: MakeUtrans 1.25 ms, VelPred 6.8 ms (interface 4.7, transverse
-// 1.2, velocities 1.0; profiles/r2_velpred_launches.csv) = 130x the reference on 16 host threads;
-// the interface stage still forms every parabola twice (once from either face).
+// registers.  256^3, ppm_type 1: MakeUtrans 1.25 ms, VelPred 5.1 ms = 175x the reference on 16
+// host threads (profiles/r2_velpred.json).
 //
 // Parity contract as in mx_device.cuh: reference expression trees (association included: the
 // 2-D and 3-D slope extrapolations differ, MaestroVelPred.cpp:336-345 vs :785-796), -fmad=false,
@@ -278,43 +278,67 @@ static void vel_pred_dim(const KGeom& g, const KVel& e, const DFab& utilde, cons
         vb.hi[q] = g.vhi[q];
     }
 
-    // ---- VelPredInterface: ul / ur of every component on the faces of mxbx / mybx / mzbx
-    // (obx with the low side of the normal direction pulled in), BCs, transverse uimh --------
+    // ---- VelPredInterface, first half: every cell forms the parabola (or slope) of each component
+    // in each direction ONCE and scatters the two traces: Im is the right state of the cell's low
+    // face, Ip the left state of its high face (ppm_type 0: the two slope extrapolations) ------
+    for_box(obx, st, [=] __device__(int i, int j, int k) {
+        const I3 c = mk(i, j, k);
+        const double dt2 = 0.5 * e.dt;
+#pragma unroll
+        for (int d = 0; d < dim; ++d) {
+            const double h = g.dx[d];
+            double fl = 0.0, fr = 0.0;
+            if (e.ppm_type == 0) {
+                const double uC = at(ufull, c, d);
+                const double uL = dmax_(0.0, uC), uR = dmin_(0.0, uC);
+                // 3-D: :785-796; 2-D association differs: :336-345
+                fl = dim == 3 ? 0.5 - dt2 * uL / h : 0.5 - (dt2 / h) * uL;
+                fr = dim == 3 ? 0.5 + dt2 * uR / h : 0.5 + (dt2 / h) * uR;
+            }
+            const bool has_hi = c.v[d] < obx.hi[d];
+            const I3 fh = sh(c, d, 1);
+#pragma unroll
+            for (int n = 0; n < dim; ++n) {
+                const RC r = recon(g, e, utilde, ufull, n, d, c);
+                double vl, vr;
+                if (e.ppm_type == 0) {
+                    const double s0 = at(utilde, c, n);
+                    vl = s0 + fl * r.ip;
+                    vr = s0 - fr * r.ip;
+                } else {
+                    vl = r.ip;
+                    vr = r.im;
+                }
+                W.ur(d, n, c) = vr;
+                if (has_hi) W.ul(d, n, fh) = vl;
+            }
+        }
+    });
+
+    // ---- VelPredInterface, second half: phys_bc on the faces of mxbx / mybx / mzbx (obx with the
+    // low side of the normal direction pulled in) and the transverse components of uimh ---------
     for_box(obx, st, [=] __device__(int i, int j, int k) {
         const I3 f = mk(i, j, k);
-        const double dt2 = 0.5 * e.dt;
 #pragma unroll
         for (int d = 0; d < dim; ++d) {
             if (f.v[d] < obx.lo[d] + 1) continue;
             const I3 cl = sh(f, d, -1);
-            const double h = g.dx[d];
             double ul[3], ur[3];
-            if (e.ppm_type == 0) {
-                const double uL = dmax_(0.0, at(ufull, cl, d)), uR = dmin_(0.0, at(ufull, f, d));
-                // 3-D: :785-796; 2-D association differs: :336-345
-                const double fl = dim == 3 ? 0.5 - dt2 * uL / h : 0.5 - (dt2 / h) * uL;
-                const double fr = dim == 3 ? 0.5 + dt2 * uR / h : 0.5 + (dt2 / h) * uR;
 #pragma unroll
-                for (int n = 0; n < dim; ++n) {
-                    ul[n] = at(utilde, cl, n) + fl * recon(g, e, utilde, ufull, n, d, cl).ip;
-                    ur[n] = at(utilde, f, n) - fr * recon(g, e, utilde, ufull, n, d, f).ip;
-                }
-            } else {
-#pragma unroll
-                for (int n = 0; n < dim; ++n) {
-                    ul[n] = recon(g, e, utilde, ufull, n, d, cl).ip;
-                    ur[n] = recon(g, e, utilde, ufull, n, d, f).im;
-                }
+            for (int n = 0; n < dim; ++n) {
+                ul[n] = W.ul(d, n, f);
+                ur[n] = W.ur(d, n, f);
             }
             const int I = f.v[d];
-            if (I == g.dlo[d]) {
+            const bool on_lo = I == g.dlo[d], on_hi = I == g.dhi[d] + 1;
+            if (on_lo) {
                 const int bc = e.pbc_lo[d];
                 if (bc == P_INFLOW) {
 #pragma unroll
                     for (int n = 0; n < dim; ++n) ul[n] = ur[n] = at(utilde, cl, n);
                 } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
-    #pragma unroll
-                for (int n = 0; n < dim; ++n) {
+#pragma unroll
+                    for (int n = 0; n < dim; ++n) {
                         if (n == d) {
                             ul[n] = 0.0;
                             ur[n] = 0.0;
@@ -329,21 +353,21 @@ static void vel_pred_dim(const KGeom& g, const KVel& e, const DFab& utilde, cons
                     ur[d] = dmin_(ur[d], 0.0);
                     if (dim == 2 && d == 0) {
                         // QUIRK: the 2-D x sweep copies left over right here (:380-385)
-    #pragma unroll
-                    for (int n = 0; n < dim; ++n) ur[n] = ul[n];
+#pragma unroll
+                        for (int n = 0; n < dim; ++n) ur[n] = ul[n];
                     } else {
-    #pragma unroll
-                    for (int n = 0; n < dim; ++n) ul[n] = ur[n];
+#pragma unroll
+                        for (int n = 0; n < dim; ++n) ul[n] = ur[n];
                     }
                 }
-            } else if (I == g.dhi[d] + 1) {
+            } else if (on_hi) {
                 const int bc = e.pbc_hi[d];
                 if (bc == P_INFLOW) {
 #pragma unroll
                     for (int n = 0; n < dim; ++n) ul[n] = ur[n] = at(utilde, f, n);
                 } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
-    #pragma unroll
-                for (int n = 0; n < dim; ++n) {
+#pragma unroll
+                    for (int n = 0; n < dim; ++n) {
                         if (n == d) {
                             ul[n] = 0.0;
                             ur[n] = 0.0;
@@ -363,8 +387,10 @@ static void vel_pred_dim(const KGeom& g, const KVel& e, const DFab& utilde, cons
             const double t = at(utr.f[d], f);
 #pragma unroll
             for (int n = 0; n < dim; ++n) {
-                W.ul(d, n, f) = ul[n];
-                W.ur(d, n, f) = ur[n];
+                if (on_lo || on_hi) {  // only boundary faces change
+                    W.ul(d, n, f) = ul[n];
+                    W.ur(d, n, f) = ur[n];
+                }
                 if (n != d) W.imh(d, n, f) = upwind_trans(t, ul[n], ur[n], e.eps);
             }
         }

@@ -1,3 +1,4 @@
-O=gpurun_out/n2final; mkdir -p $O
-timeout -k 10 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -rs 2>&1 | tail -8 | cut -c1-200 | tee $O/pytest_multi.log
-timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 5 --warmup 3 > $O/bench_n2_512.json 2> $O/bench_n2.err; tail -c 600 $O/bench_n2_512.json
+O=gpurun_out/vp5; mkdir -p $O
+timeout -k 10 600 python -m pytest tests/test_velpred.py -q -m gpu -x 2>&1 | tail -3 | cut -c1-300 | tee $O/pytest_velpred.log
+timeout -k 10 300 python tools/bench_velpred.py --size 256 --ppm 1 --cpu-size 0 | tee $O/velpred_256_ppm1.json
+timeout -k 10 300 python tools/bench_velpred.py --size 256 --ppm 0 --cpu-size 0 | tee $O/velpred_256_ppm0.json
