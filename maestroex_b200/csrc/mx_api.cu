@@ -2,6 +2,7 @@
 // residency (device / managed / host), stream-ordered device workspace, host staging, and
 // dispatch to the fused (mx_fused.cu) or staged (mx_staged.cu) kernels.  No CPU compute
 // path exists: without a CUDA device every compute entry point returns MX_ERR_NO_DEVICE.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1613,6 +1614,13 @@ static int vel_params(const MxGeom* g, const MxVelPredParams* p, KVel* e) {
     e->slope_order = p->slope_order;
     e->trace = p->ppm_trace_forces != 0;
     e->spherical = p->spherical != 0;
+    for (int d = 0; d < 3; ++d) {
+        const double h = d < g->dim ? g->dx[d] : 1.0;
+        int ex = 0;
+        e->h[d] = h;
+        e->inv_h[d] = 1.0 / h;
+        e->inv_exact[d] = std::frexp(h, &ex) == 0.5 ? 1 : 0;  // power of two: x * (1/h) is exact
+    }
     for (int d = 0; d < g->dim; ++d) {
         e->pbc_lo[d] = p->phys_bc_lo[d];
         e->pbc_hi[d] = p->phys_bc_hi[d];

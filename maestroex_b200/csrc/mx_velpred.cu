@@ -18,7 +18,7 @@
 // i fastest; four launches per VelPred call (three in 2-D), one per direction for MakeUtrans.
 // Kernels are instantiated per dimension with the direction / component loops unrolled, so that
 // fab descriptors are read from the kernel parameters and the small per-thread arrays live in
-// registers.  256^3, ppm_type 1: MakeUtrans 1.25 ms, VelPred 5.1 ms = 175x the reference on 16
+// registers.  256^3, ppm_type 1: MakeUtrans 1.25 ms, VelPred 4.6 ms = 190x the reference on 16
 // host threads (profiles/r2_velpred.json).
 //
 // Parity contract as in mx_device.cuh: reference expression trees (association included: the
@@ -41,19 +41,30 @@ struct Box3 {
 };
 
 template <class F>
-__global__ void __launch_bounds__(128) k_vbox(Box3 b, F f) {
-    const int i = b.lo[0] + blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(256) k_vbox(Box3 b, F f) {
+    const int i = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = b.lo[1] + blockIdx.y;
     const int k = b.lo[2] + blockIdx.z;
     if (i <= b.hi[0]) f(i, j, k);
 }
 
+// one thread per zone, i fastest.  The block width is chosen per box: a row of 258 zones (a 256^3
+// box grown by one) would leave a third of three 128-thread blocks idle, three 96-thread blocks
+// lose 10 % (256^3 ran 15 % slower per zone than 250^3 with fixed 128-thread blocks)
 template <class F>
 void for_box(const Box3& b, cudaStream_t st, F f) {
     const int nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
     if (nx <= 0 || ny <= 0 || nz <= 0) return;
-    dim3 grid((nx + 127) / 128, ny, nz);
-    k_vbox<<<grid, 128, 0, st>>>(b, f);
+    int bw = 128, best = 1 << 30;
+    for (int w = 64; w <= 256; w += 32) {
+        const int padded = (nx + w - 1) / w * w;
+        if (padded < best || (padded == best && w > bw)) {
+            best = padded;
+            bw = w;
+        }
+    }
+    dim3 grid((nx + bw - 1) / bw, ny, nz);
+    k_vbox<<<grid, bw, 0, st>>>(b, f);
     mx_count_launch();
 }
 
@@ -118,6 +129,21 @@ WS make_ws(const KGeom& g, double* p) {
     return w;
 }
 
+// x / h_d, correctly rounded (== the IEEE division of the reference): the sequence of div_h in
+// mx_stream.cuh (tests/test_divconst.py), ~5 fp64 instructions instead of a software division
+MXD double div_hd(const KVel& e, int d, double x) {
+    const double y = e.inv_h[d];
+    double q = x * y;
+    if (!e.inv_exact[d]) {
+        const double h = e.h[d];
+        double r = fma_(-h, q, x);
+        q = fma_(r, y, q);
+        r = fma_(-h, q, x);
+        q = fma_(r, y, q);
+    }
+    return q;
+}
+
 // Slopex/y/z (ppm_type 0: `ip` is the slope) or PPM with is_umac = false of component n of `s`
 // in direction d at cell c; bcs_u[n] decides the one-sided rows (MaestroSlopes.cpp:17-22,
 // MaestroPPM.cpp:30-31)
@@ -150,7 +176,7 @@ MXD RC recon(const KGeom& g, const KVel& e, const DFab& s, const DFab& uf, int n
     const double u = at(uf, c, d);
     const double s0 = S[3];
     const double s6 = 6.0 * s0 - 3.0 * (sm + sp);
-    const double sig = fabs(u) * e.dt / g.dx[d];
+    const double sig = div_hd(e, d, fabs(u) * e.dt);
     r.ip = ppm_Ip(sm, sp, s0, s6, u, sig, e.eps);
     r.im = ppm_Im(sm, sp, s0, s6, u, sig, e.eps);
     return r;

@@ -11,6 +11,9 @@ struct KVel {
     int ppm_type, slope_order, trace, spherical;
     int pbc_lo[3], pbc_hi[3];
     int bclo[3][3], bchi[3][3];  // [component][direction]
+    // x / h_d as a correctly rounded multiply-and-refine sequence (mx_stream.cuh: div_h)
+    double h[3], inv_h[3];
+    int inv_exact[3];
 };
 
 // doubles of device workspace vel_pred() needs for this box
