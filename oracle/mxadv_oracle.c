@@ -369,7 +369,7 @@ static inline void cs_limit(double sedgel, double sedge, double sedger, double s
 }
 
 static void ppm_dir(const Ctx* c, int d, const CView* s, const CView* vel, Tmp* Ip, Tmp* Im,
-                    int bclo, int bchi) {
+                    int bclo, int bchi, int is_umac) {
     const int e0 = d == 0, e1 = d == 1, e2 = d == 2;
     const int lo = c->domlo[d], hi = c->domhi[d];
     const int lobc = (bclo == BC_EXT_DIR || bclo == BC_HOEXTRAP);
@@ -461,9 +461,10 @@ static void ppm_dir(const Ctx* c, int d, const CView* s, const CView* vel, Tmp* 
                 }
             }
         }
-        /* MaestroPPM.cpp:210-231 (is_umac) */
+        /* MaestroPPM.cpp:210-231 (is_umac: MAC velocity, edge-based indexing) / :233-251 (cell-
+         * centred velocity: both integrals use u(i,j,k); MakeUtrans and VelPred) */
         const double s6 = 6.0 * s0 - 3.0 * (sm + sp);
-        const double up = RD(*vel, i + e0, j + e1, k + e2);
+        const double up = is_umac ? RD(*vel, i + e0, j + e1, k + e2) : RD(*vel, i, j, k);
         const double um = RD(*vel, i, j, k);
         double sigma = fabs(up) * dt / h;
         if (up > eps) {
@@ -824,9 +825,9 @@ int orc_make_edge_scal(const MxGeom* g, const MxFab* state, const MxFab* sedge,
             if (c.ppm_type == 0) {
                 slope_dir(&c, d, &s, &Ip[d], bc[d], bc[3 + d]); /* :207-216 */
             } else {
-                ppm_dir(&c, d, &s, &vel[d], &Ip[d], &Im[d], bc[d], bc[3 + d]); /* :219-221 */
+                ppm_dir(&c, d, &s, &vel[d], &Ip[d], &Im[d], bc[d], bc[3 + d], 1); /* :219-221 */
                 if (c.ppm_trace_forces == 1) {
-                    ppm_dir(&c, d, &fv, &vel[d], &Ipf[d], &Imf[d], bc[d], bc[3 + d]);
+                    ppm_dir(&c, d, &fv, &vel[d], &Ipf[d], &Imf[d], bc[d], bc[3 + d], 1);
                 }
             }
         }
@@ -1534,3 +1535,376 @@ int orc_make_w0_planar_ml(const MxW0Params* p, const MxRadialGeom* rg, const dou
 }
 #undef RS
 #undef RE
+
+/* ==================================================================================== */
+/* MAC-velocity predictor                                   */
+/*   Source/MaestroMakeUtrans.cpp:6-648    -> orc_make_utrans()                           */
+/*   Source/MaestroVelPred.cpp:5-1917      -> orc_vel_pred(): VelPredInterface (:296-542  */
+/*      2-D, :735-1128 3-D), VelPredTransverse (:1130-1595), VelPredVelocities (:544-733  */
+/*      2-D, :1597-1917 3-D)                                                               */
+/* Staged like the reference: Ip / Im (or slopes) of every velocity component in every     */
+/* direction first, then the interface states, the corner-coupled states, the velocities. */
+/* Pinned bit for bit against the reference's own translation units compiled into          */
+/* oracle/_ref (tests/test_velpred.py).                                                    */
+/* ==================================================================================== */
+enum { P_INTERIOR = 0, P_INFLOW = 1, P_OUTFLOW = 2, P_SYMMETRY = 3, P_SLIPWALL = 4, P_NOSLIPWALL = 5 };
+
+typedef struct {
+    Ctx c;
+    int spherical, trace;
+    int pbc_lo[3], pbc_hi[3];
+    int bclo[3][3], bchi[3][3]; /* [component][direction] */
+} VCtx;
+
+static int fill_vctx(VCtx* v, const MxGeom* g, const MxVelPredParams* p) {
+    if (!g || !p || !p->bc) return -1;
+    memset(v, 0, sizeof(*v));
+    Ctx* c = &v->c;
+    c->dim = g->dim;
+    for (int d = 0; d < 3; ++d) {
+        const int in = d < g->dim;
+        c->valid.lo[d] = in ? g->valid_lo[d] : 0;
+        c->valid.hi[d] = in ? g->valid_hi[d] : 0;
+        c->domlo[d] = in ? g->dom_lo[d] : 0;
+        c->domhi[d] = in ? g->dom_hi[d] : 0;
+        c->dx[d] = in ? g->dx[d] : 1.0;
+    }
+    c->obx = grow_all(c->valid, 1, g->dim);
+    c->dt = p->dt;
+    c->rel_eps = p->rel_eps;
+    c->ppm_type = p->ppm_type;
+    c->slope_order = p->slope_order;
+    v->spherical = p->spherical != 0;
+    v->trace = p->ppm_trace_forces != 0;
+    for (int d = 0; d < g->dim; ++d) {
+        v->pbc_lo[d] = p->phys_bc_lo[d];
+        v->pbc_hi[d] = p->phys_bc_hi[d];
+        for (int n = 0; n < g->dim; ++n) {
+            v->bclo[n][d] = p->bc[6 * n + d];
+            v->bchi[n][d] = p->bc[6 * n + 3 + d];
+        }
+    }
+    return 0;
+}
+
+/* Slopex/y/z or PPM(is_umac = false) of component n of `s` in direction d over obx */
+static void vrecon(const VCtx* v, const MxFab* s, const MxFab* ufull, int n, int d, Tmp* Ip, Tmp* Im) {
+    const CView sv = cview(s, n), uv = cview(ufull, d);
+    if (v->c.ppm_type == 0)
+        slope_dir(&v->c, d, &sv, Ip, v->bclo[n][d], v->bchi[n][d]);
+    else
+        ppm_dir(&v->c, d, &sv, &uv, Ip, Im, v->bclo[n][d], v->bchi[n][d], 0);
+}
+
+/* w0 term of the Riemann problems at face (i,j,k) of direction d */
+static double v_w0(const VCtx* v, const MxFab* w0_cart, const MxFab* w0mac, int d, int i, int j, int k) {
+    if (v->spherical) return *fab_at(&w0mac[d], i, j, k, 0);
+    if (d == v->c.dim - 1) return *fab_at(w0_cart, i, j, k, v->c.dim - 1);
+    return 0.0;
+}
+
+static double v_riemann(double l, double r, double w, double eps) {
+    const int test = (l + w <= 0.0 && r + w >= 0.0) || (fabs(l + r + 2.0 * w) < eps);
+    const double val = 0.5 * (l + r) + w > 0.0 ? l : r;
+    return test ? 0.0 : val;
+}
+
+static double v_upwind(double t, double l, double r, double eps) {
+    const double val = t > 0.0 ? l : r;
+    return fabs(t) < eps ? 0.5 * (l + r) : val;
+}
+
+int orc_make_utrans(const MxGeom* g, const MxFab* utilde, const MxFab* ufull, const MxFab* utrans,
+                    const MxFab* w0_cart, const MxFab* w0mac, const MxVelPredParams* p) {
+    VCtx v;
+    if (fill_vctx(&v, g, p)) return -1;
+    const Ctx* c = &v.c;
+    const int dim = c->dim;
+    const double dt2 = 0.5 * c->dt;
+    for (int d = 0; d < dim; ++d) {
+        const int e[3] = {d == 0, d == 1, d == 2};
+        Tmp Ip = tmp_alloc(c->obx), Im = tmp_alloc(c->obx);
+        vrecon(&v, utilde, ufull, d, d, &Ip, &Im);
+        IBox fb = c->valid;
+        fb.hi[d] += 1;
+        for (int k = fb.lo[2]; k <= fb.hi[2]; ++k)
+        for (int j = fb.lo[1]; j <= fb.hi[1]; ++j)
+        for (int i = fb.lo[0]; i <= fb.hi[0]; ++i) {
+            const int il = i - e[0], jl = j - e[1], kl = k - e[2];
+            const int I = d == 0 ? i : (d == 1 ? j : k);
+            double l, r;
+            if (c->ppm_type == 0) { /* MaestroMakeUtrans.cpp:94-103 */
+                l = *fab_at(utilde, il, jl, kl, d) +
+                    (0.5 - (dt2 / c->dx[d]) * dmax(0.0, *fab_at(ufull, il, jl, kl, d))) * T(Ip, il, jl, kl);
+                r = *fab_at(utilde, i, j, k, d) -
+                    (0.5 + (dt2 / c->dx[d]) * dmin(0.0, *fab_at(ufull, i, j, k, d))) * T(Ip, i, j, k);
+            } else {
+                l = T(Ip, il, jl, kl);
+                r = T(Im, i, j, k);
+            }
+            if (I == c->domlo[d]) {
+                const int bc = v.pbc_lo[d];
+                if (bc == P_INFLOW) {
+                    l = r = *fab_at(utilde, il, jl, kl, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    /* QUIRK: the 2-D y sweep zeroes only the right state (:220-221) */
+                    if (!(dim == 2 && d == 1)) l = 0.0;
+                    r = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    l = dmin(r, 0.0);
+                    r = l;
+                }
+            } else if (I == c->domhi[d] + 1) {
+                const int bc = v.pbc_hi[d];
+                if (bc == P_INFLOW) {
+                    /* QUIRK: the 3-D sweeps read one cell further out (:350-351, :466-467, :581-582) */
+                    const int q = dim == 3 ? 1 : 0;
+                    l = r = *fab_at(utilde, i + q * e[0], j + q * e[1], k + q * e[2], d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    l = 0.0;
+                    r = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    l = dmax(l, 0.0);
+                    r = l;
+                }
+            }
+            *fab_at(&utrans[d], i, j, k, 0) =
+                v_riemann(l, r, v_w0(&v, w0_cart, w0mac, d, i, j, k), c->rel_eps);
+        }
+        free(Ip.p);
+        free(Im.p);
+    }
+    return 0;
+}
+
+int orc_vel_pred(const MxGeom* g, const MxFab* utilde, const MxFab* ufull, const MxFab* utrans,
+                 const MxFab* umac, const MxFab* w0mac, const MxFab* w0_cart, const MxFab* force,
+                 const MxVelPredParams* p) {
+    VCtx v;
+    if (fill_vctx(&v, g, p)) return -1;
+    const Ctx* c = &v.c;
+    const int dim = c->dim;
+    if (v.trace && (dim == 2 || c->ppm_type == 0)) return -2; /* see mx_vel_pred */
+    const double dt2 = 0.5 * c->dt, dt4 = 0.25 * c->dt, dt6 = c->dt / 6.0, eps = c->rel_eps;
+    const IBox obx = c->obx;
+    /* Ip / Im of component n in direction d ([n][d]; ppm_type 0: the slope is in Ip) */
+    Tmp Ip[3][3], Im[3][3], Ipf[3], Imf[3], ul[3][3], ur[3][3], imh[3][3], tr[3][3];
+    memset(Ipf, 0, sizeof(Ipf));
+    memset(Imf, 0, sizeof(Imf));
+    memset(tr, 0, sizeof(tr));
+    for (int n = 0; n < dim; ++n)
+        for (int d = 0; d < dim; ++d) {
+            Ip[n][d] = tmp_alloc(obx);
+            Im[n][d] = tmp_alloc(obx);
+            ul[d][n] = tmp_alloc(obx);
+            ur[d][n] = tmp_alloc(obx);
+            imh[d][n] = tmp_alloc(obx);
+            vrecon(&v, utilde, ufull, n, d, &Ip[n][d], &Im[n][d]);
+        }
+    if (v.trace)
+        for (int d = 0; d < dim; ++d) {
+            Ipf[d] = tmp_alloc(obx);
+            Imf[d] = tmp_alloc(obx);
+            vrecon(&v, force, ufull, d, d, &Ipf[d], &Imf[d]);
+        }
+
+    /* ---- VelPredInterface ---- */
+    for (int d = 0; d < dim; ++d) {
+        const int e[3] = {d == 0, d == 1, d == 2};
+        const double h = c->dx[d];
+        IBox mb = obx;
+        mb.lo[d] += 1;
+        CView tv = cview(&utrans[d], 0);
+        for (int k = mb.lo[2]; k <= mb.hi[2]; ++k)
+        for (int j = mb.lo[1]; j <= mb.hi[1]; ++j)
+        for (int i = mb.lo[0]; i <= mb.hi[0]; ++i) {
+            const int il = i - e[0], jl = j - e[1], kl = k - e[2];
+            const int I = d == 0 ? i : (d == 1 ? j : k);
+            double l[3], r[3];
+            if (c->ppm_type == 0) {
+                const double uL = dmax(0.0, *fab_at(ufull, il, jl, kl, d));
+                const double uR = dmin(0.0, *fab_at(ufull, i, j, k, d));
+                /* 3-D: :785-796; the 2-D association differs: :336-345 */
+                const double fl = dim == 3 ? 0.5 - dt2 * uL / h : 0.5 - (dt2 / h) * uL;
+                const double fr = dim == 3 ? 0.5 + dt2 * uR / h : 0.5 + (dt2 / h) * uR;
+                for (int n = 0; n < dim; ++n) {
+                    l[n] = *fab_at(utilde, il, jl, kl, n) + fl * T(Ip[n][d], il, jl, kl);
+                    r[n] = *fab_at(utilde, i, j, k, n) - fr * T(Ip[n][d], i, j, k);
+                }
+            } else {
+                for (int n = 0; n < dim; ++n) {
+                    l[n] = T(Ip[n][d], il, jl, kl);
+                    r[n] = T(Im[n][d], i, j, k);
+                }
+            }
+            if (I == c->domlo[d]) {
+                const int bc = v.pbc_lo[d];
+                if (bc == P_INFLOW) {
+                    for (int n = 0; n < dim; ++n) l[n] = r[n] = *fab_at(utilde, il, jl, kl, n);
+                } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
+                    for (int n = 0; n < dim; ++n) {
+                        if (n == d) {
+                            l[n] = 0.0;
+                            r[n] = 0.0;
+                        } else {
+                            l[n] = r[n];
+                        }
+                    }
+                } else if (bc == P_NOSLIPWALL) {
+                    for (int n = 0; n < dim; ++n) l[n] = r[n] = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    r[d] = dmin(r[d], 0.0);
+                    if (dim == 2 && d == 0) { /* QUIRK: the 2-D x sweep copies left over right (:380-385) */
+                        for (int n = 0; n < dim; ++n) r[n] = l[n];
+                    } else {
+                        for (int n = 0; n < dim; ++n) l[n] = r[n];
+                    }
+                }
+            } else if (I == c->domhi[d] + 1) {
+                const int bc = v.pbc_hi[d];
+                if (bc == P_INFLOW) {
+                    for (int n = 0; n < dim; ++n) l[n] = r[n] = *fab_at(utilde, i, j, k, n);
+                } else if (bc == P_SLIPWALL || bc == P_SYMMETRY) {
+                    for (int n = 0; n < dim; ++n) {
+                        if (n == d) {
+                            l[n] = 0.0;
+                            r[n] = 0.0;
+                        } else {
+                            r[n] = l[n];
+                        }
+                    }
+                } else if (bc == P_NOSLIPWALL) {
+                    for (int n = 0; n < dim; ++n) l[n] = r[n] = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    l[d] = dmax(l[d], 0.0);
+                    for (int n = 0; n < dim; ++n) r[n] = l[n];
+                }
+            }
+            const double t = RD(tv, i, j, k);
+            for (int n = 0; n < dim; ++n) {
+                T(ul[d][n], i, j, k) = l[n];
+                T(ur[d][n], i, j, k) = r[n];
+                if (n != d) T(imh[d][n], i, j, k) = v_upwind(t, l[n], r[n], eps);
+            }
+        }
+    }
+
+    /* ---- VelPredTransverse (3-D): component n on d faces, corrected in direction t ---- */
+    if (dim == 3) {
+        for (int n = 0; n < 3; ++n)
+        for (int d = 0; d < 3; ++d) {
+            if (d == n) continue;
+            const int t = 3 - n - d;
+            const int e[3] = {d == 0, d == 1, d == 2}, q[3] = {t == 0, t == 1, t == 2};
+            tr[n][d] = tmp_alloc(obx);
+            IBox b = c->valid; /* amrex::grow(tilebox, n, 1), growHi(d, 1) */
+            b.lo[n] -= 1;
+            b.hi[n] += 1;
+            b.hi[d] += 1;
+            const CView tt = cview(&utrans[t], 0), td = cview(&utrans[d], 0);
+            const double ht = c->dx[t];
+            for (int k = b.lo[2]; k <= b.hi[2]; ++k)
+            for (int j = b.lo[1]; j <= b.hi[1]; ++j)
+            for (int i = b.lo[0]; i <= b.hi[0]; ++i) {
+                const int il = i - e[0], jl = j - e[1], kl = k - e[2];
+                const int I = d == 0 ? i : (d == 1 ? j : k);
+                double l = T(ul[d][n], i, j, k) -
+                           (dt6 / ht) * (RD(tt, il + q[0], jl + q[1], kl + q[2]) + RD(tt, il, jl, kl)) *
+                               (T(imh[t][n], il + q[0], jl + q[1], kl + q[2]) - T(imh[t][n], il, jl, kl));
+                double r = T(ur[d][n], i, j, k) -
+                           (dt6 / ht) * (RD(tt, i + q[0], j + q[1], k + q[2]) + RD(tt, i, j, k)) *
+                               (T(imh[t][n], i + q[0], j + q[1], k + q[2]) - T(imh[t][n], i, j, k));
+                if (I == c->domlo[d]) {
+                    const int bc = v.pbc_lo[d];
+                    if (bc == P_INFLOW) {
+                        l = r = *fab_at(utilde, il, jl, kl, n);
+                    } else if (bc == P_SLIPWALL || bc == P_SYMMETRY || bc == P_OUTFLOW) {
+                        l = r;
+                    } else if (bc == P_NOSLIPWALL) {
+                        l = r = 0.0;
+                    }
+                } else if (I == c->domhi[d] + 1) {
+                    const int bc = v.pbc_hi[d];
+                    if (bc == P_INFLOW) {
+                        l = r = *fab_at(utilde, i, j, k, n);
+                    } else if (bc == P_SLIPWALL || bc == P_SYMMETRY || bc == P_OUTFLOW) {
+                        r = l;
+                    } else if (bc == P_NOSLIPWALL) {
+                        l = r = 0.0;
+                    }
+                }
+                T(tr[n][d], i, j, k) = v_upwind(RD(td, i, j, k), l, r, eps);
+            }
+        }
+    }
+
+    /* ---- VelPredVelocities ---- */
+    for (int d = 0; d < dim; ++d) {
+        const int e[3] = {d == 0, d == 1, d == 2};
+        IBox fb = c->valid;
+        fb.hi[d] += 1;
+        for (int k = fb.lo[2]; k <= fb.hi[2]; ++k)
+        for (int j = fb.lo[1]; j <= fb.hi[1]; ++j)
+        for (int i = fb.lo[0]; i <= fb.hi[0]; ++i) {
+            const int il = i - e[0], jl = j - e[1], kl = k - e[2];
+            const int I = d == 0 ? i : (d == 1 ? j : k);
+            double fl, fr;
+            if (!v.trace) {
+                fl = *fab_at(force, il, jl, kl, d);
+                fr = *fab_at(force, i, j, k, d);
+            } else {
+                fl = T(Ipf[d], il, jl, kl);
+                fr = T(Imf[d], i, j, k);
+            }
+            double l = T(ul[d][d], i, j, k), r = T(ur[d][d], i, j, k);
+            for (int t = 0; t < dim; ++t) { /* the transverse directions in ascending order */
+                if (t == d) continue;
+                const int q[3] = {t == 0, t == 1, t == 2};
+                const CView tt = cview(&utrans[t], 0);
+                const Tmp* a = dim == 3 ? &tr[d][t] : &imh[t][d];
+                const double ht = c->dx[t];
+                l = l - (dt4 / ht) * (RD(tt, il + q[0], jl + q[1], kl + q[2]) + RD(tt, il, jl, kl)) *
+                            (T(*a, il + q[0], jl + q[1], kl + q[2]) - T(*a, il, jl, kl));
+                r = r - (dt4 / ht) * (RD(tt, i + q[0], j + q[1], k + q[2]) + RD(tt, i, j, k)) *
+                            (T(*a, i + q[0], j + q[1], k + q[2]) - T(*a, i, j, k));
+            }
+            l = l + dt2 * fl;
+            r = r + dt2 * fr;
+            double val = v_riemann(l, r, v_w0(&v, w0_cart, w0mac, d, i, j, k), eps);
+            if (I == c->domlo[d]) {
+                const int bc = v.pbc_lo[d];
+                if (bc == P_INFLOW) {
+                    val = *fab_at(utilde, il, jl, kl, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    val = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    val = dmin(r, 0.0);
+                }
+            } else if (I == c->domhi[d] + 1) {
+                const int bc = v.pbc_hi[d];
+                if (bc == P_INFLOW) {
+                    val = *fab_at(utilde, i, j, k, d);
+                } else if (bc == P_SLIPWALL || bc == P_NOSLIPWALL || bc == P_SYMMETRY) {
+                    val = 0.0;
+                } else if (bc == P_OUTFLOW) {
+                    val = dmax(l, 0.0);
+                }
+            }
+            *fab_at(&umac[d], i, j, k, 0) = val;
+        }
+    }
+    for (int n = 0; n < dim; ++n)
+        for (int d = 0; d < dim; ++d) {
+            free(Ip[n][d].p);
+            free(Im[n][d].p);
+            free(ul[d][n].p);
+            free(ur[d][n].p);
+            free(imh[d][n].p);
+            free(tr[n][d].p);
+        }
+    for (int d = 0; d < 3; ++d) {
+        free(Ipf[d].p);
+        free(Imf[d].p);
+    }
+    return 0;
+}

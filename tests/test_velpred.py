@@ -1,16 +1,17 @@
 """MAC-velocity predictor: Maestro::MakeUtrans and Maestro::VelPred.
 
-The checker for these two members is the REFERENCE ITSELF: Source/MaestroMakeUtrans.cpp and
-Source/MaestroVelPred.cpp compiled unmodified into oracle/_ref/libmaestro_ref{2,3}d.so
-(oracle/Makefile), plus golden vectors generated from it (tests/golden/velpred_*.npz, written
-by tests/golden/make_golden_velpred.py) for machines where oracle/_ref is absent.
+Checkers: (i) the REFERENCE ITSELF, Source/MaestroMakeUtrans.cpp and Source/MaestroVelPred.cpp
+compiled unmodified into oracle/_ref/libmaestro_ref{2,3}d.so (oracle/Makefile); (ii) the plain-C
+restatement orc_make_utrans / orc_vel_pred (oracle/mxadv_oracle.c), staged like the reference;
+(iii) golden vectors generated from (i) (tests/golden/velpred_*.npz, written by
+tests/golden/make_golden_velpred.py).
 
-CPU (``not gpu``): the committed goldens are reproduced by the compiled reference (when present)
-and are self-consistent (shapes, finite values).
-GPU: libmxadv.so (mx_velpred.cu) through the C ABI against the compiled reference on every case
-(2-D / 3-D, ppm_type 0/1/2, slope_order 0/2/4, every phys_bc code, planar / spherical,
-ppm_trace_forces, box on the domain faces and strictly inside) and against the goldens, bit for
-bit, with device- and host-resident fabs."""
+CPU (``not gpu``): the C oracle against the compiled reference on every case, bit for bit -> the
+oracle is pinned; the committed goldens are reproduced by the compiled reference and by the oracle.
+GPU: libmxadv.so (mx_velpred.cu) through the C ABI against the oracle, the compiled reference and
+the goldens on every case (2-D / 3-D, ppm_type 0/1/2, slope_order 0/2/4, every phys_bc code,
+planar / spherical, ppm_trace_forces, box on the domain faces and strictly inside), bit for bit,
+with device- and host-resident fabs."""
 import os
 
 import numpy as np
@@ -161,6 +162,22 @@ def test_golden_reproduced_by_reference(name, runner, kw, ref2d, ref3d):
         same(a, b, f"{name}[{q}] reference vs committed golden")
 
 
+@pytest.mark.parametrize("name,runner,kw", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_reference(name, runner, kw, oracle_calls, ref2d, ref3d):
+    ref = ref2d if kw["dim"] == 2 else ref3d
+    want = runner(ref, **kw)
+    got = runner(oracle_calls, **kw)
+    for q, (a, b) in enumerate(zip(got, want)):
+        same(a, b, f"{name}[{q}] oracle vs reference")
+
+
+@pytest.mark.parametrize("name,runner,kw", GOLDEN, ids=[c[0] for c in GOLDEN])
+def test_oracle_matches_golden(name, runner, kw, oracle_calls):
+    got = runner(oracle_calls, **kw)
+    for q, (a, b) in enumerate(zip(got, load_golden(name))):
+        same(a, b, f"{name}[{q}] oracle vs committed golden")
+
+
 @pytest.mark.parametrize("name,runner,kw", GOLDEN, ids=[c[0] for c in GOLDEN])
 def test_golden_files_sane(name, runner, kw):
     outs = load_golden(name)
@@ -212,6 +229,15 @@ def test_cuda_matches_reference(name, runner, kw, residency, mx, ref2d, ref3d):
     got = _run_mx(mx, runner, kw, residency)
     for q, (a, b) in enumerate(zip(got, want)):
         same(a, b, f"{name}[{q}] CUDA ({residency}) vs reference")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,runner,kw", CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_oracle(name, runner, kw, mx, oracle_calls):
+    want = runner(oracle_calls, **kw)
+    got = _run_mx(mx, runner, kw, "device")
+    for q, (a, b) in enumerate(zip(got, want)):
+        same(a, b, f"{name}[{q}] CUDA vs oracle")
 
 
 @pytest.mark.gpu
