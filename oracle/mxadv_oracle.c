@@ -30,6 +30,9 @@
  *   Source/MaestroMakew0.cpp:5-58,60-272    -> orc_make_w0_planar() (one radial level)
  *   Source/MaestroMakew0.cpp:537-740,942-969 + Source/MaestroMakeGrav.cpp:303-322
  *                                           -> orc_make_w0_sphr()
+ *   Source/MaestroMakeUtrans.cpp:6-648      -> orc_make_utrans()
+ *   Source/MaestroVelPred.cpp:5-1917        -> orc_vel_pred()  (tests/test_velpred.py pins both
+ *                                              to MaestroMakeUtrans.cpp / MaestroVelPred.cpp in _ref)
  * Direction-dependent quirks of the reference that are reproduced on purpose are marked
  * "QUIRK" with the file:line they come from.
  */
